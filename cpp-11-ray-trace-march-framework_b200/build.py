@@ -1,0 +1,60 @@
+"""Build the native libraries of this package in-tree (nvcc / g++, sm_100a only).
+
+    python cpp-11-ray-trace-march-framework_b200/build.py [--force]
+
+libcuda_trace.so  -- CUDA kernels + the C ABI of include/cuda_trace.h (csrc/*.cu)
+"""
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB_CUDA = os.path.join(PKG, "libcuda_trace.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# -fmad=false: the kernels must round like the reference's FMA-free x86-64 build
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-Xptxas", "-v"]
+CU_SOURCES = ["api.cu", "trace_kernels.cu", "pack.cu", "grid_build.cu"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_cuda(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(ROOT, "include", "cuda_trace.h"))
+    if not force and not _newer(LIB_CUDA, deps):
+        return LIB_CUDA
+    objs = []
+    for s in srcs:
+        o = s[:-3] + ".o"
+        if force or _newer(o, deps):
+            cmd = [NVCC] + NVCC_FLAGS + ["-c", s, "-o", o]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or r.returncode:
+                sys.stderr.write(r.stdout + r.stderr)
+            if r.returncode:
+                raise RuntimeError("nvcc failed: " + " ".join(cmd))
+            with open(o + ".ptxas.log", "w") as f:
+                f.write(r.stdout + r.stderr)
+        objs.append(o)
+    cmd = [NVCC, "-shared", "-o", LIB_CUDA] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    subprocess.check_call(cmd)
+    return LIB_CUDA
+
+
+def build_all(force=False, verbose=False):
+    return [build_cuda(force, verbose)]
+
+
+if __name__ == "__main__":
+    print("\n".join(build_all("--force" in sys.argv, "-v" in sys.argv)))

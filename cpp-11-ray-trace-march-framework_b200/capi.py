@@ -1,0 +1,288 @@
+"""ctypes binding of include/cuda_trace.h (libcuda_trace.so) -- the reference-facing boundary.
+
+There is no fallback of any kind: if the CUDA library is missing, or no B200 is present,
+``CudaTrace()`` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libcuda_trace.so")
+
+MISS = 0xFFFFFFFF
+VARIANT_MT = 0
+VARIANT_BARY = 1
+FLAG_GAMMA = 1
+FLAG_KEEP_HITS = 2
+
+_F32P = C.POINTER(C.c_float)
+_U32P = C.POINTER(C.c_uint32)
+_U64P = C.POINTER(C.c_uint64)
+
+
+class Frame(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("variant", C.c_uint32),
+                ("flags", C.c_uint32), ("fov_xs", C.c_float), ("aspect", C.c_float), ("cam_mat", C.c_float * 16)]
+
+
+class TileRect(C.Structure):
+    _fields_ = [("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32)]
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("dim", C.c_uint32 * 3), ("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3),
+                ("cell_wdh", C.c_float), ("inv_cell_wdh", C.c_float), ("num_cells", C.c_uint64),
+                ("num_refs", C.c_uint64)]
+
+
+class CountersC(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("cells", C.c_uint64), ("tri_tests", C.c_uint64), ("hits", C.c_uint64)]
+
+
+# every symbol include/cuda_trace.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "cuda_trace_init": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "cuda_trace_init_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "cuda_trace_destroy": (None, [C.c_void_p]),
+    "cuda_trace_last_error": (C.c_char_p, [C.c_void_p]),
+    "cuda_trace_device_count": (C.c_int, []),
+    "cuda_trace_set_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "cuda_trace_upload_scene": (C.c_int, [C.c_void_p, _F32P, C.c_uint32, _U32P, C.c_uint32, C.c_uint32]),
+    "cuda_trace_upload_scene_with_grid": (C.c_int, [C.c_void_p, _F32P, C.c_uint32, _U32P, C.c_uint32,
+                                                    C.POINTER(GridDesc), _U64P, _U32P]),
+    "cuda_trace_download_grid": (C.c_int, [C.c_void_p, C.POINTER(GridDesc), _U64P, _U32P]),
+    "cuda_trace_tiles": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.POINTER(TileRect), C.c_uint32, _U32P]),
+    "cuda_trace_tiles_async": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.POINTER(TileRect), C.c_uint32]),
+    "cuda_trace_sync": (C.c_int, [C.c_void_p]),
+    "cuda_trace_read_framebuffer": (C.c_int, [C.c_void_p, _U32P]),
+    "cuda_trace_cancel": (C.c_int, [C.c_void_p]),
+    "cuda_trace_last_kernel_ms": (C.c_int, [C.c_void_p, _F32P]),
+    "cuda_trace_download_hits": (C.c_int, [C.c_void_p, _U32P, _F32P, _F32P, _F32P]),
+    "cuda_trace_intersect_rays": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, C.c_uint32, _U32P, _F32P,
+                                            _F32P, _F32P]),
+    "cuda_trace_sample_table": (C.c_int, [C.c_void_p, C.c_uint32, _F32P]),
+    "cuda_trace_set_counting": (C.c_int, [C.c_void_p, C.c_int]),
+    "cuda_trace_get_counters": (C.c_int, [C.c_void_p, C.POINTER(CountersC)]),
+    "cuda_trace_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "cuda_trace_prepare_framebuffer": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "cuda_trace_export_framebuffer": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cuda_trace_import_framebuffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "cuda_trace_framebuffer_device_ptr": (C.c_void_p, [C.c_void_p]),
+    "cuda_trace_stream": (C.c_void_p, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen libcuda_trace.so and bind every declared symbol.  Raises if the library is absent:
+    the product path has no other implementation to fall back to."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(LIB_PATH + " is missing: build it with "
+                               "`python cpp-11-ray-trace-march-framework_b200/build.py` "
+                               "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class CudaTraceError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cuda_trace error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def full_frame_tiles(width, height, tiles_x=12, tiles_y=9):
+    """The reference's fixed 12 x 9 tile layout (framebuffer.h:87-88, framebuffer.cpp:106-117):
+    tile size = floor(size / count), the last column / row absorbs the remainder."""
+    tw, th = width // tiles_x, height // tiles_y
+    out = []
+    for y in range(tiles_y):
+        for x in range(tiles_x):
+            out.append((x * tw, y * th, width if x == tiles_x - 1 else (x + 1) * tw,
+                        height if y == tiles_y - 1 else (y + 1) * th))
+    return out
+
+
+class CudaTrace:
+    """One cuda_trace_ctx.  ``n_gpus`` devices (0..n-1) or an explicit ``devices`` list."""
+
+    def __init__(self, n_gpus=1, devices=None):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.cuda_trace_init_devices(arr, len(devices), C.byref(self.h))
+        else:
+            rc = self.lib.cuda_trace_init(n_gpus, C.byref(self.h))
+        if rc:
+            msg = self.lib.cuda_trace_last_error(None).decode()
+            self.h = None
+            raise CudaTraceError(rc, msg)
+        self._pinned = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cuda_trace_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc):
+        if rc:
+            raise CudaTraceError(rc, self.lib.cuda_trace_last_error(self.h).decode())
+
+    # -- scene
+    def upload_scene(self, vtx, tri, grid_res=64):
+        vtx = np.ascontiguousarray(vtx, np.float32)
+        tri = np.ascontiguousarray(tri, np.uint32)
+        self._ck(self.lib.cuda_trace_upload_scene(self.h, _p(vtx, _F32P), len(vtx), _p(tri, _U32P), len(tri), grid_res))
+
+    def upload_scene_with_grid(self, vtx, tri, grid):
+        vtx = np.ascontiguousarray(vtx, np.float32)
+        tri = np.ascontiguousarray(tri, np.uint32)
+        d = GridDesc()
+        for k in range(3):
+            d.dim[k] = int(grid["dim"][k])
+            d.aabb_min[k] = float(grid["aabb_min"][k])
+            d.aabb_max[k] = float(grid["aabb_max"][k])
+        d.cell_wdh = float(grid["cell_wdh"])
+        d.inv_cell_wdh = float(grid["inv_cell_wdh"])
+        off = np.ascontiguousarray(grid["cell_offset"], np.uint64)
+        idx = np.ascontiguousarray(grid["tri_index"], np.uint32)
+        d.num_cells = len(off) - 1
+        d.num_refs = len(idx)
+        self._ck(self.lib.cuda_trace_upload_scene_with_grid(self.h, _p(vtx, _F32P), len(vtx), _p(tri, _U32P),
+                                                            len(tri), C.byref(d), _p(off, _U64P),
+                                                            _p(idx, _U32P) if len(idx) else None))
+
+    def download_grid(self):
+        d = GridDesc()
+        self._ck(self.lib.cuda_trace_download_grid(self.h, C.byref(d), None, None))
+        off = np.zeros(d.num_cells + 1, np.uint64)
+        idx = np.zeros(max(int(d.num_refs), 1), np.uint32)
+        self._ck(self.lib.cuda_trace_download_grid(self.h, C.byref(d), _p(off, _U64P), _p(idx, _U32P)))
+        return dict(dim=np.array(list(d.dim), np.uint32), aabb_min=np.array(list(d.aabb_min), np.float32),
+                    aabb_max=np.array(list(d.aabb_max), np.float32), cell_wdh=np.float32(d.cell_wdh),
+                    inv_cell_wdh=np.float32(d.inv_cell_wdh), cell_offset=off, tri_index=idx[:int(d.num_refs)])
+
+    # -- frames
+    @staticmethod
+    def make_frame(width, height, spp, cam16, fov_xs, aspect, variant=VARIANT_MT, gamma=True, keep_hits=False):
+        f = Frame()
+        f.width, f.height, f.spp, f.variant = width, height, spp, variant
+        f.flags = (FLAG_GAMMA if gamma else 0) | (FLAG_KEEP_HITS if keep_hits else 0)
+        f.fov_xs, f.aspect = float(fov_xs), float(aspect)
+        cam16 = np.asarray(cam16, np.float32).reshape(16)
+        for i in range(16):
+            f.cam_mat[i] = float(cam16[i])
+        return f
+
+    @staticmethod
+    def make_tiles(rects):
+        arr = (TileRect * max(len(rects), 1))()
+        for i, r in enumerate(rects):
+            arr[i].x0, arr[i].y0, arr[i].x1, arr[i].y1 = [int(v) for v in r]
+        return arr
+
+    def trace_tiles(self, frame, rects=None, out=None, want_image=True):
+        """Render ``rects`` (default: the reference's 12x9 layout of the whole frame) and return
+        the host image [H, W] uint32 (row 0 = y 0)."""
+        if rects is None:
+            rects = full_frame_tiles(frame.width, frame.height)
+        tiles = self.make_tiles(rects)
+        if want_image and out is None:
+            out = np.zeros((frame.height, frame.width), np.uint32)
+        self._ck(self.lib.cuda_trace_tiles(self.h, C.byref(frame), tiles, len(rects),
+                                           _p(out, _U32P) if want_image else None))
+        return out
+
+    def trace_tiles_async(self, frame, rects=None):
+        if rects is None:
+            rects = full_frame_tiles(frame.width, frame.height)
+        tiles = self.make_tiles(rects)
+        self._ck(self.lib.cuda_trace_tiles_async(self.h, C.byref(frame), tiles, len(rects)))
+
+    def sync(self):
+        self._ck(self.lib.cuda_trace_sync(self.h))
+
+    def read_framebuffer(self, out):
+        self._ck(self.lib.cuda_trace_read_framebuffer(self.h, _p(out, _U32P)))
+        return out
+
+    def cancel(self):
+        self._ck(self.lib.cuda_trace_cancel(self.h))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._ck(self.lib.cuda_trace_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def download_hits(self, width, height, spp, want_tuv=True):
+        shape = (height, width, spp)
+        tri = np.empty(shape, np.uint32)
+        t = np.empty(shape, np.float32) if want_tuv else None
+        u = np.empty(shape, np.float32) if want_tuv else None
+        v = np.empty(shape, np.float32) if want_tuv else None
+        self._ck(self.lib.cuda_trace_download_hits(self.h, _p(tri, _U32P), _p(t, _F32P), _p(u, _F32P), _p(v, _F32P)))
+        return tri, t, u, v
+
+    def intersect_rays(self, origins, dirs, variant=VARIANT_MT):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = len(o)
+        tri, t, u, v = (np.empty(n, np.uint32), np.empty(n, np.float32), np.empty(n, np.float32),
+                        np.empty(n, np.float32))
+        self._ck(self.lib.cuda_trace_intersect_rays(self.h, n, _p(o, _F32P), _p(d, _F32P), variant,
+                                                    _p(tri, _U32P), _p(t, _F32P), _p(u, _F32P), _p(v, _F32P)))
+        return tri, t, u, v
+
+    def sample_table(self, spp):
+        xy = np.zeros((spp, 2), np.float32)
+        self._ck(self.lib.cuda_trace_sample_table(self.h, spp, _p(xy, _F32P)))
+        return xy
+
+    def set_counting(self, enable):
+        self._ck(self.lib.cuda_trace_set_counting(self.h, int(enable)))
+
+    def get_counters(self):
+        c = CountersC()
+        self._ck(self.lib.cuda_trace_get_counters(self.h, C.byref(c)))
+        return dict(rays=int(c.rays), cells=int(c.cells), tri_tests=int(c.tri_tests), hits=int(c.hits))
+
+    def kernel_launches(self):
+        return int(self.lib.cuda_trace_kernel_launches(self.h))
+
+    def set_shard(self, rank, world):
+        self._ck(self.lib.cuda_trace_set_shard(self.h, rank, world))
+
+    def prepare_framebuffer(self, width, height):
+        self._ck(self.lib.cuda_trace_prepare_framebuffer(self.h, width, height))
+
+    def export_framebuffer(self):
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.cuda_trace_export_framebuffer(self.h, buf))
+        return buf.raw
+
+    def import_framebuffer(self, handle, width, height):
+        buf = C.create_string_buffer(bytes(handle), 64)
+        self._ck(self.lib.cuda_trace_import_framebuffer(self.h, buf, width, height))
+
+    def framebuffer_device_ptr(self):
+        return self.lib.cuda_trace_framebuffer_device_ptr(self.h)
+
+    def stream(self):
+        return self.lib.cuda_trace_stream(self.h)

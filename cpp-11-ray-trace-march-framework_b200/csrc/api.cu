@@ -1,0 +1,876 @@
+// C ABI of the tile tracer (include/cuda_trace.h): contexts, scene upload, frame launches.
+//
+// This is the "thin launch layer" that replaces the reference's worker-thread tile pool
+// (framebuffer.cpp:16-92): a frame is one persistent-kernel launch per device instead of
+// hardware_concurrency() threads popping tiles from a mutex-protected queue.
+#include "../../include/cuda_trace.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "grid_build.cuh"
+#include "trace_kernels.cuh"
+
+using namespace rtm;
+
+namespace
+{
+
+std::string g_init_error;
+
+struct DeviceState
+{
+    int ordinal = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr; // cancel flag writes while the main stream is busy
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+
+    // scene
+    float *d_vtx = nullptr;
+    uint32_t *d_tri = nullptr;
+    uint32_t *d_cell_start = nullptr, *d_cell_occ = nullptr, *d_tri_index = nullptr;
+    float4 *d_cell_tris = nullptr, *d_cell_tris_b = nullptr, *d_tri_normals = nullptr;
+
+    // frame
+    float2 *d_smp = nullptr;
+    uint32_t smp_cap = 0, smp_valid_spp = 0;
+    uint4 *d_tile_rects = nullptr;
+    uint32_t *d_tile_prefix = nullptr;
+    uint32_t tile_cap = 0;
+    uint32_t *d_strip_counter = nullptr;
+    uint32_t *d_cancel = nullptr;
+    Counters *d_counters = nullptr;
+    bool frame_pending = false;
+};
+
+} // namespace
+
+struct cuda_trace_ctx
+{
+    std::vector<DeviceState> dev;
+    std::string err;
+    std::mutex cancel_mtx;
+
+    bool have_scene = false;
+    cuda_trace_grid_desc desc;
+    uint32_t num_vtx = 0, num_tri = 0;
+
+    uint32_t shard_rank = 0, shard_world = 1;
+    bool counting = false;
+    std::atomic<uint64_t> launches{0};
+
+    // framebuffer (device 0, or an imported IPC mapping of another process' framebuffer)
+    uint32_t *d_fb = nullptr;
+    bool fb_imported = false;
+    uint32_t fb_w = 0, fb_h = 0;
+
+    // per-sample hit records of the last KEEP_HITS frame (device 0)
+    uint32_t *d_hit_tri = nullptr;
+    float *d_hit_t = nullptr, *d_hit_u = nullptr, *d_hit_v = nullptr;
+    uint64_t hit_cap = 0, hit_count = 0;
+
+    // last frame
+    cuda_trace_frame frame;
+    std::vector<cuda_trace_tile_rect> tiles;
+    bool frame_valid = false;
+    float last_kernel_ms = 0.0f;
+    uint32_t *pinned_cancel_src = nullptr;
+
+    // cached registration of the caller's host framebuffer
+    void *registered_host = nullptr;
+    size_t registered_bytes = 0;
+};
+
+namespace
+{
+
+int fail(cuda_trace_ctx *ctx, int code, const std::string& msg)
+{
+    if (ctx)
+        ctx->err = msg;
+    else
+        g_init_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(ctx, CUDA_TRACE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+void free_scene(DeviceState& d)
+{
+    cudaSetDevice(d.ordinal);
+    cudaFree(d.d_vtx); cudaFree(d.d_tri); cudaFree(d.d_cell_start); cudaFree(d.d_cell_occ);
+    cudaFree(d.d_tri_index); cudaFree(d.d_cell_tris); cudaFree(d.d_cell_tris_b); cudaFree(d.d_tri_normals);
+    d.d_vtx = nullptr; d.d_tri = nullptr; d.d_cell_start = nullptr; d.d_cell_occ = nullptr;
+    d.d_tri_index = nullptr; d.d_cell_tris = nullptr; d.d_cell_tris_b = nullptr; d.d_tri_normals = nullptr;
+}
+
+GridDev grid_dev(const cuda_trace_ctx *ctx, const DeviceState& d)
+{
+    GridDev g;
+    for (int k = 0; k < 3; k++)
+    {
+        g.dim[k] = ctx->desc.dim[k];
+        g.aabb_min[k] = ctx->desc.aabb_min[k];
+        g.aabb_max[k] = ctx->desc.aabb_max[k];
+    }
+    g.cell_wdh = ctx->desc.cell_wdh;
+    g.inv_cell_wdh = ctx->desc.inv_cell_wdh;
+    g.cell_start = d.d_cell_start;
+    g.cell_occ = d.d_cell_occ;
+    g.cell_tris = d.d_cell_tris;
+    g.cell_tris_b = d.d_cell_tris_b;
+    g.tri_normals = d.d_tri_normals;
+    return g;
+}
+
+// After d_vtx / d_tri / d_cell_start / d_tri_index are in place on device d: derived layout
+int finish_scene_on_device(cuda_trace_ctx *ctx, DeviceState& d)
+{
+    const uint64_t cells = ctx->desc.num_cells, refs = ctx->desc.num_refs;
+    CK(cudaMalloc(&d.d_cell_occ, ((cells + 31) / 32) * sizeof(uint32_t)));
+    CK(cudaMalloc(&d.d_cell_tris, std::max<uint64_t>(refs, 1) * 3 * sizeof(float4)));
+    CK(cudaMalloc(&d.d_cell_tris_b, std::max<uint64_t>(refs, 1) * 2 * sizeof(float4)));
+    CK(cudaMalloc(&d.d_tri_normals, (size_t) ctx->num_tri * 3 * sizeof(float4)));
+    launch_cell_occupancy(d.d_cell_start, cells, d.d_cell_occ, d.stream);
+    launch_pack_cell_tris(d.d_vtx, d.d_tri, d.d_tri_index, refs, d.d_cell_tris, d.d_cell_tris_b, d.stream);
+    launch_pack_normals(d.d_vtx, d.d_tri, ctx->num_tri, d.d_tri_normals, d.stream);
+    ctx->launches += 2 + (refs ? 1 : 0);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(d.stream));
+    return 0;
+}
+
+int upload_mesh(cuda_trace_ctx *ctx, DeviceState& d, const float *vertices, uint32_t num_vertices,
+                const uint32_t *triangles, uint32_t num_triangles)
+{
+    CK(cudaSetDevice(d.ordinal));
+    CK(cudaMalloc(&d.d_vtx, (size_t) num_vertices * 24));
+    CK(cudaMalloc(&d.d_tri, (size_t) num_triangles * 24));
+    CK(cudaMemcpyAsync(d.d_vtx, vertices, (size_t) num_vertices * 24, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d.d_tri, triangles, (size_t) num_triangles * 24, cudaMemcpyHostToDevice, d.stream));
+    return 0;
+}
+
+int check_mesh_args(cuda_trace_ctx *ctx, const float *vertices, uint32_t num_vertices, const uint32_t *triangles,
+                    uint32_t num_triangles)
+{
+    if (!ctx)
+        return CUDA_TRACE_ERR_ARG;
+    if (!vertices || !triangles || num_vertices == 0 || num_triangles == 0)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "upload_scene: empty mesh (the reference asserts, grid.cpp:15)");
+    for (uint32_t i = 0; i < num_triangles; i++)
+        for (int c = 0; c < 3; c++)
+            if (triangles[(size_t) i * 6 + c] >= num_vertices)
+                return fail(ctx, CUDA_TRACE_ERR_ARG, "upload_scene: vertex index out of bounds");
+    return 0;
+}
+
+int ensure_framebuffer(cuda_trace_ctx *ctx, uint32_t w, uint32_t h)
+{
+    if (ctx->d_fb && ctx->fb_w == w && ctx->fb_h == h)
+        return 0;
+    if (ctx->fb_imported)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "frame size differs from the imported framebuffer");
+    CK(cudaSetDevice(ctx->dev[0].ordinal));
+    if (ctx->d_fb)
+        CK(cudaFree(ctx->d_fb));
+    ctx->d_fb = nullptr;
+    CK(cudaMalloc(&ctx->d_fb, (size_t) w * h * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(ctx->d_fb, 0, (size_t) w * h * sizeof(uint32_t), ctx->dev[0].stream));
+    ctx->fb_w = w;
+    ctx->fb_h = h;
+    return 0;
+}
+
+} // namespace
+
+extern "C"
+{
+
+int cuda_trace_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+int cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **out)
+{
+    cuda_trace_ctx *ctx = nullptr;
+    if (!out || n < 1 || !device_ordinals)
+        return fail(nullptr, CUDA_TRACE_ERR_ARG, "cuda_trace_init: bad arguments");
+    *out = nullptr;
+    int have = 0;
+    cudaError_t e = cudaGetDeviceCount(&have);
+    if (e != cudaSuccess || have < 1)
+        return fail(nullptr, CUDA_TRACE_ERR_NO_DEVICE,
+                    std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    for (int i = 0; i < n; i++)
+        if (device_ordinals[i] < 0 || device_ordinals[i] >= have)
+            return fail(nullptr, CUDA_TRACE_ERR_NO_DEVICE, "requested device ordinal " +
+                        std::to_string(device_ordinals[i]) + " but only " + std::to_string(have) + " present");
+
+    ctx = new cuda_trace_ctx();
+    std::memset(&ctx->desc, 0, sizeof(ctx->desc));
+    std::memset(&ctx->frame, 0, sizeof(ctx->frame));
+    ctx->dev.resize(n);
+    auto bail = [&](const std::string& msg, int code) {
+        g_init_error = msg;
+        cuda_trace_destroy(ctx);
+        return code;
+    };
+    for (int i = 0; i < n; i++)
+    {
+        DeviceState& d = ctx->dev[i];
+        d.ordinal = device_ordinals[i];
+        cudaDeviceProp prop;
+        if ((e = cudaSetDevice(d.ordinal)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, d.ordinal)) != cudaSuccess)
+            return bail(std::string("cudaSetDevice/GetDeviceProperties: ") + cudaGetErrorString(e), CUDA_TRACE_ERR_CUDA);
+        if (prop.major < 10)
+            return bail("device " + std::to_string(d.ordinal) + " (" + prop.name + ") is sm_" +
+                        std::to_string(prop.major * 10 + prop.minor) + "; this library is built for sm_100a only",
+                        CUDA_TRACE_ERR_NO_DEVICE);
+        d.sm_count = prop.multiProcessorCount;
+        if ((e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&d.side_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreate(&d.ev_begin)) != cudaSuccess || (e = cudaEventCreate(&d.ev_end)) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_strip_counter, sizeof(uint32_t))) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_cancel, sizeof(uint32_t))) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_counters, sizeof(Counters))) != cudaSuccess ||
+            (e = cudaMemset(d.d_cancel, 0, sizeof(uint32_t))) != cudaSuccess ||
+            (e = cudaMemset(d.d_counters, 0, sizeof(Counters))) != cudaSuccess)
+            return bail(std::string("device set-up: ") + cudaGetErrorString(e), CUDA_TRACE_ERR_CUDA);
+        if (i > 0)
+        {
+            // strips rendered on device i are stored straight into device 0's framebuffer
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, d.ordinal, ctx->dev[0].ordinal);
+            if (!can)
+                return bail("device " + std::to_string(d.ordinal) + " cannot access device " +
+                            std::to_string(ctx->dev[0].ordinal) + " as a peer", CUDA_TRACE_ERR_NO_DEVICE);
+            e = cudaDeviceEnablePeerAccess(ctx->dev[0].ordinal, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled)
+                cudaGetLastError();
+            else if (e != cudaSuccess)
+                return bail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e), CUDA_TRACE_ERR_CUDA);
+        }
+    }
+    if ((e = cudaHostAlloc(&ctx->pinned_cancel_src, sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
+        return bail(std::string("cudaHostAlloc: ") + cudaGetErrorString(e), CUDA_TRACE_ERR_CUDA);
+    *ctx->pinned_cancel_src = 1;
+    *out = ctx;
+    return 0;
+}
+
+int cuda_trace_init(int n_gpus, cuda_trace_ctx **out)
+{
+    if (n_gpus < 1 || n_gpus > 64)
+        return fail(nullptr, CUDA_TRACE_ERR_ARG, "cuda_trace_init: n_gpus must be 1..64");
+    int ids[64];
+    for (int i = 0; i < n_gpus; i++)
+        ids[i] = i;
+    return cuda_trace_init_devices(ids, n_gpus, out);
+}
+
+void cuda_trace_destroy(cuda_trace_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    for (DeviceState& d : ctx->dev)
+    {
+        cudaSetDevice(d.ordinal);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+    }
+    if (ctx->registered_host)
+        cudaHostUnregister(ctx->registered_host);
+    if (!ctx->dev.empty())
+    {
+        cudaSetDevice(ctx->dev[0].ordinal);
+        if (ctx->d_fb)
+        {
+            if (ctx->fb_imported) cudaIpcCloseMemHandle(ctx->d_fb); else cudaFree(ctx->d_fb);
+        }
+        cudaFree(ctx->d_hit_tri); cudaFree(ctx->d_hit_t); cudaFree(ctx->d_hit_u); cudaFree(ctx->d_hit_v);
+    }
+    for (DeviceState& d : ctx->dev)
+    {
+        free_scene(d);
+        cudaFree(d.d_smp); cudaFree(d.d_tile_rects); cudaFree(d.d_tile_prefix); cudaFree(d.d_strip_counter);
+        cudaFree(d.d_cancel); cudaFree(d.d_counters);
+        if (d.ev_begin) cudaEventDestroy(d.ev_begin);
+        if (d.ev_end) cudaEventDestroy(d.ev_end);
+        if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.side_stream) cudaStreamDestroy(d.side_stream);
+    }
+    if (ctx->pinned_cancel_src)
+        cudaFreeHost(ctx->pinned_cancel_src);
+    delete ctx;
+}
+
+const char *cuda_trace_last_error(const cuda_trace_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+uint64_t cuda_trace_kernel_launches(const cuda_trace_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int cuda_trace_set_shard(cuda_trace_ctx *ctx, uint32_t rank, uint32_t world)
+{
+    if (!ctx)
+        return CUDA_TRACE_ERR_ARG;
+    if (world == 0 || rank >= world)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "set_shard: need rank < world");
+    ctx->shard_rank = rank;
+    ctx->shard_world = world;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- scene
+int cuda_trace_upload_scene(cuda_trace_ctx *ctx, const float *vertices, uint32_t num_vertices,
+                            const uint32_t *triangles, uint32_t num_triangles, uint32_t grid_res)
+{
+    int rc = check_mesh_args(ctx, vertices, num_vertices, triangles, num_triangles);
+    if (rc)
+        return rc;
+    if (grid_res == 0)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "upload_scene: grid_res must be > 0 (grid.cpp:16)");
+    if ((rc = cuda_trace_sync(ctx)))
+        return rc;
+    ctx->have_scene = false;
+    ctx->num_vtx = num_vertices;
+    ctx->num_tri = num_triangles;
+    for (size_t i = 0; i < ctx->dev.size(); i++)
+    {
+        DeviceState& d = ctx->dev[i];
+        free_scene(d);
+        if ((rc = upload_mesh(ctx, d, vertices, num_vertices, triangles, num_triangles)))
+            return rc;
+        // Every device builds its own copy of the grid (the build is deterministic and cheaper
+        // than shipping the cell-major records over NVLink would be to code; ~ms)
+        GridBuildResult res;
+        uint64_t launches = 0;
+        std::string err;
+        rc = build_grid_device(d.d_vtx, num_vertices, d.d_tri, num_triangles, grid_res, d.stream, &res, err, &launches);
+        ctx->launches += launches;
+        if (rc)
+            return fail(ctx, rc, err);
+        d.d_cell_start = res.d_cell_start;
+        d.d_tri_index = res.d_tri_index;
+        if (i == 0)
+            ctx->desc = res.desc;
+        else if (std::memcmp(&ctx->desc, &res.desc, sizeof(res.desc)) != 0)
+            return fail(ctx, CUDA_TRACE_ERR_CUDA, "grid build differs between devices");
+        if ((rc = finish_scene_on_device(ctx, d)))
+            return rc;
+    }
+    ctx->have_scene = true;
+    return 0;
+}
+
+int cuda_trace_upload_scene_with_grid(cuda_trace_ctx *ctx, const float *vertices, uint32_t num_vertices,
+                                      const uint32_t *triangles, uint32_t num_triangles,
+                                      const cuda_trace_grid_desc *desc, const uint64_t *cell_offset,
+                                      const uint32_t *tri_index)
+{
+    int rc = check_mesh_args(ctx, vertices, num_vertices, triangles, num_triangles);
+    if (rc)
+        return rc;
+    if (!desc || !cell_offset || (!tri_index && desc->num_refs))
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "upload_scene_with_grid: null grid arrays");
+    const uint64_t cells = (uint64_t) desc->dim[0] * desc->dim[1] * desc->dim[2];
+    if (cells == 0 || cells != desc->num_cells || cells >= (1ull << 31) || desc->num_refs >= (1ull << 32) ||
+        cell_offset[0] != 0 || cell_offset[cells] != desc->num_refs)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "upload_scene_with_grid: inconsistent grid description");
+    for (uint64_t c = 0; c < cells; c++)
+        if (cell_offset[c] > cell_offset[c + 1])
+            return fail(ctx, CUDA_TRACE_ERR_ARG, "upload_scene_with_grid: cell_offset not monotone");
+    for (uint64_t k = 0; k < desc->num_refs; k++)
+        if (tri_index[k] >= num_triangles)
+            return fail(ctx, CUDA_TRACE_ERR_ARG, "upload_scene_with_grid: triangle index out of bounds");
+    if ((rc = cuda_trace_sync(ctx)))
+        return rc;
+    ctx->have_scene = false;
+    ctx->num_vtx = num_vertices;
+    ctx->num_tri = num_triangles;
+    ctx->desc = *desc;
+    for (DeviceState& d : ctx->dev)
+    {
+        free_scene(d);
+        if ((rc = upload_mesh(ctx, d, vertices, num_vertices, triangles, num_triangles)))
+            return rc;
+        uint64_t *d_off64 = nullptr;
+        CK(cudaMalloc(&d_off64, (cells + 1) * sizeof(uint64_t)));
+        CK(cudaMalloc(&d.d_cell_start, (cells + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc(&d.d_tri_index, std::max<uint64_t>(desc->num_refs, 1) * sizeof(uint32_t)));
+        CK(cudaMemcpyAsync(d_off64, cell_offset, (cells + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
+        if (desc->num_refs)
+            CK(cudaMemcpyAsync(d.d_tri_index, tri_index, desc->num_refs * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                               d.stream));
+        launch_narrow_offsets(d_off64, cells + 1, d.d_cell_start, d.stream);
+        ctx->launches++;
+        CK(cudaStreamSynchronize(d.stream));
+        CK(cudaFree(d_off64));
+        if ((rc = finish_scene_on_device(ctx, d)))
+            return rc;
+    }
+    ctx->have_scene = true;
+    return 0;
+}
+
+int cuda_trace_download_grid(cuda_trace_ctx *ctx, cuda_trace_grid_desc *desc, uint64_t *cell_offset,
+                             uint32_t *tri_index)
+{
+    if (!ctx || !desc)
+        return CUDA_TRACE_ERR_ARG;
+    if (!ctx->have_scene)
+        return fail(ctx, CUDA_TRACE_ERR_NO_SCENE, "download_grid: no scene uploaded");
+    *desc = ctx->desc;
+    DeviceState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.ordinal));
+    if (cell_offset)
+    {
+        uint64_t *d_off64 = nullptr;
+        CK(cudaMalloc(&d_off64, (ctx->desc.num_cells + 1) * sizeof(uint64_t)));
+        launch_widen_offsets(d.d_cell_start, ctx->desc.num_cells + 1, d_off64, d.stream);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(cell_offset, d_off64, (ctx->desc.num_cells + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                           d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        CK(cudaFree(d_off64));
+    }
+    if (tri_index && ctx->desc.num_refs)
+    {
+        CK(cudaMemcpyAsync(tri_index, d.d_tri_index, ctx->desc.num_refs * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                           d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------- tracing
+int cuda_trace_prepare_framebuffer(cuda_trace_ctx *ctx, uint32_t width, uint32_t height)
+{
+    if (!ctx || width == 0 || height == 0)
+        return CUDA_TRACE_ERR_ARG;
+    int rc = ensure_framebuffer(ctx, width, height);
+    if (rc)
+        return rc;
+    CK(cudaStreamSynchronize(ctx->dev[0].stream));
+    return 0;
+}
+
+int cuda_trace_export_framebuffer(cuda_trace_ctx *ctx, void *handle64)
+{
+    if (!ctx || !handle64)
+        return CUDA_TRACE_ERR_ARG;
+    if (!ctx->d_fb || ctx->fb_imported)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "export_framebuffer: call cuda_trace_prepare_framebuffer first");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaSetDevice(ctx->dev[0].ordinal));
+    CK(cudaIpcGetMemHandle(&h, ctx->d_fb));
+    std::memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int cuda_trace_import_framebuffer(cuda_trace_ctx *ctx, const void *handle64, uint32_t width, uint32_t height)
+{
+    if (!ctx || !handle64 || width == 0 || height == 0)
+        return CUDA_TRACE_ERR_ARG;
+    int rc = cuda_trace_sync(ctx);
+    if (rc)
+        return rc;
+    CK(cudaSetDevice(ctx->dev[0].ordinal));
+    if (ctx->d_fb)
+    {
+        if (ctx->fb_imported) CK(cudaIpcCloseMemHandle(ctx->d_fb)); else CK(cudaFree(ctx->d_fb));
+        ctx->d_fb = nullptr;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->d_fb = (uint32_t *) p;
+    ctx->fb_imported = true;
+    ctx->fb_w = width;
+    ctx->fb_h = height;
+    return 0;
+}
+
+void *cuda_trace_framebuffer_device_ptr(cuda_trace_ctx *ctx) { return ctx ? ctx->d_fb : nullptr; }
+void *cuda_trace_stream(cuda_trace_ctx *ctx) { return (ctx && !ctx->dev.empty()) ? (void *) ctx->dev[0].stream : nullptr; }
+
+int cuda_trace_set_counting(cuda_trace_ctx *ctx, int enable)
+{
+    if (!ctx)
+        return CUDA_TRACE_ERR_ARG;
+    ctx->counting = enable != 0;
+    return 0;
+}
+
+int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const cuda_trace_tile_rect *tiles,
+                           uint32_t n_tiles)
+{
+    if (!ctx || !f || (!tiles && n_tiles))
+        return CUDA_TRACE_ERR_ARG;
+    if (!ctx->have_scene)
+        return fail(ctx, CUDA_TRACE_ERR_NO_SCENE, "trace_tiles: upload a scene first");
+    if (f->width == 0 || f->height == 0 || f->spp == 0 || f->variant > 1)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: bad frame description");
+    if ((uint64_t) f->width * f->height >= (1ull << 32))
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: frame too large");
+    int rc = cuda_trace_sync(ctx); // one frame in flight per context
+    if (rc && rc != CUDA_TRACE_ERR_CANCELLED)
+        return rc;
+
+    // strips per tile (8 x 4 pixel blocks, clipped to the tile)
+    std::vector<uint4> rects(n_tiles);
+    std::vector<uint32_t> prefix(n_tiles + 1, 0);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_tiles; i++)
+    {
+        const cuda_trace_tile_rect& t = tiles[i];
+        if (t.x0 > t.x1 || t.y0 > t.y1 || t.x1 > f->width || t.y1 > f->height)
+            return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: tile " + std::to_string(i) + " outside the frame");
+        rects[i] = make_uint4(t.x0, t.y0, t.x1, t.y1);
+        prefix[i] = (uint32_t) total;
+        total += (uint64_t) ((t.x1 - t.x0 + kStripW - 1) / kStripW) * ((t.y1 - t.y0 + kStripH - 1) / kStripH);
+        if (total >= (1ull << 32))
+            return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: too many strips");
+    }
+    prefix[n_tiles] = (uint32_t) total;
+
+    if ((rc = ensure_framebuffer(ctx, f->width, f->height)))
+        return rc;
+    const bool keep_hits = (f->flags & CUDA_TRACE_FLAG_KEEP_HITS) != 0;
+    if (keep_hits)
+    {
+        const uint64_t need = (uint64_t) f->width * f->height * f->spp;
+        if (need > ctx->hit_cap)
+        {
+            CK(cudaSetDevice(ctx->dev[0].ordinal));
+            cudaFree(ctx->d_hit_tri); cudaFree(ctx->d_hit_t); cudaFree(ctx->d_hit_u); cudaFree(ctx->d_hit_v);
+            ctx->d_hit_tri = nullptr; ctx->d_hit_t = ctx->d_hit_u = ctx->d_hit_v = nullptr;
+            ctx->hit_cap = 0;
+            CK(cudaMalloc(&ctx->d_hit_tri, need * 4));
+            CK(cudaMalloc(&ctx->d_hit_t, need * 4));
+            CK(cudaMalloc(&ctx->d_hit_u, need * 4));
+            CK(cudaMalloc(&ctx->d_hit_v, need * 4));
+            ctx->hit_cap = need;
+        }
+        ctx->hit_count = need;
+        CK(cudaSetDevice(ctx->dev[0].ordinal));
+        // samples outside the requested tiles read as "miss"
+        CK(cudaMemsetAsync(ctx->d_hit_tri, 0xFF, need * 4, ctx->dev[0].stream));
+        CK(cudaMemsetAsync(ctx->d_hit_t, 0, need * 4, ctx->dev[0].stream));
+        CK(cudaMemsetAsync(ctx->d_hit_u, 0, need * 4, ctx->dev[0].stream));
+        CK(cudaMemsetAsync(ctx->d_hit_v, 0, need * 4, ctx->dev[0].stream));
+        CK(cudaStreamSynchronize(ctx->dev[0].stream));
+    }
+    else
+        ctx->hit_count = 0;
+    if (ctx->dev.size() > 1)
+        CK(cudaStreamSynchronize(ctx->dev[0].stream)); // framebuffer (re)allocation visible to peers
+
+    ctx->frame = *f;
+    ctx->tiles.assign(tiles, tiles + n_tiles);
+    ctx->frame_valid = true;
+
+    const uint32_t n_dev = (uint32_t) ctx->dev.size();
+    for (uint32_t i = 0; i < n_dev; i++)
+    {
+        DeviceState& d = ctx->dev[i];
+        CK(cudaSetDevice(d.ordinal));
+        if (d.smp_cap < f->spp)
+        {
+            cudaFree(d.d_smp);
+            d.d_smp = nullptr;
+            CK(cudaMalloc(&d.d_smp, sizeof(float2) * f->spp));
+            d.smp_cap = f->spp;
+            d.smp_valid_spp = 0;
+        }
+        if (d.smp_valid_spp != f->spp)
+        {
+            launch_sample_table(d.d_smp, f->spp, d.stream); // K2
+            ctx->launches++;
+            d.smp_valid_spp = f->spp;
+        }
+        if (d.tile_cap < n_tiles + 1)
+        {
+            cudaFree(d.d_tile_rects); cudaFree(d.d_tile_prefix);
+            d.d_tile_rects = nullptr; d.d_tile_prefix = nullptr;
+            d.tile_cap = std::max<uint32_t>(n_tiles + 1, 128);
+            CK(cudaMalloc(&d.d_tile_rects, sizeof(uint4) * d.tile_cap));
+            CK(cudaMalloc(&d.d_tile_prefix, sizeof(uint32_t) * d.tile_cap));
+        }
+        if (n_tiles)
+            CK(cudaMemcpyAsync(d.d_tile_rects, rects.data(), sizeof(uint4) * n_tiles, cudaMemcpyHostToDevice, d.stream));
+        CK(cudaMemcpyAsync(d.d_tile_prefix, prefix.data(), sizeof(uint32_t) * (n_tiles + 1), cudaMemcpyHostToDevice,
+                           d.stream));
+        CK(cudaMemsetAsync(d.d_strip_counter, 0, sizeof(uint32_t), d.stream));
+        CK(cudaMemsetAsync(d.d_cancel, 0, sizeof(uint32_t), d.stream));
+        if (ctx->counting)
+            CK(cudaMemsetAsync(d.d_counters, 0, sizeof(Counters), d.stream));
+        // rects / prefix are pageable host vectors: the async copies above have consumed them
+        // only once the stream reaches them, so wait before they go out of scope
+        CK(cudaStreamSynchronize(d.stream));
+
+        TraceParams p;
+        p.grid = grid_dev(ctx, d);
+        for (int r = 0; r < 3; r++)
+        {
+            for (int c = 0; c < 3; c++)
+                p.cam.m[r][c] = f->cam_mat[r * 4 + c];
+            p.cam.origin[r] = f->cam_mat[12 + r];
+        }
+        p.cam.fov_xs = f->fov_xs;
+        p.cam.aspect = f->aspect;
+        p.cam.width_f = (float) f->width;
+        p.cam.height_f = (float) f->height;
+        p.width = f->width;
+        p.height = f->height;
+        p.spp = f->spp;
+        p.gamma = (f->flags & CUDA_TRACE_FLAG_GAMMA) ? 1u : 0u;
+        p.smp = d.d_smp;
+        p.tile_rects = d.d_tile_rects;
+        p.tile_strip_prefix = d.d_tile_prefix;
+        p.n_tiles = n_tiles;
+        p.total_strips = (uint32_t) total;
+        // strips are interleaved first over the processes (shard), then over this context's devices
+        p.shard_world = ctx->shard_world * n_dev;
+        p.shard_rank = ctx->shard_rank * n_dev + i;
+        p.strip_counter = d.d_strip_counter;
+        p.cancel = d.d_cancel;
+        p.framebuffer = ctx->d_fb;
+        p.hit_tri = keep_hits ? ctx->d_hit_tri : nullptr;
+        p.hit_t = keep_hits ? ctx->d_hit_t : nullptr;
+        p.hit_u = keep_hits ? ctx->d_hit_u : nullptr;
+        p.hit_v = keep_hits ? ctx->d_hit_v : nullptr;
+        p.counters = d.d_counters;
+
+        const int per_sm = std::max(1, trace_tiles_max_blocks_per_sm(f->variant, keep_hits, ctx->counting));
+        const uint64_t my_strips = (total + p.shard_world - 1) / p.shard_world;
+        const uint64_t want = (my_strips + (kTraceThreads / 32) - 1) / (kTraceThreads / 32);
+        const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) d.sm_count * per_sm, want));
+        CK(cudaEventRecord(d.ev_begin, d.stream));
+        if (total)
+        {
+            launch_trace_tiles(p, f->variant, keep_hits, ctx->counting, blocks, d.stream);
+            ctx->launches++;
+        }
+        CK(cudaEventRecord(d.ev_end, d.stream));
+        CK(cudaGetLastError());
+        d.frame_pending = true;
+    }
+    return 0;
+}
+
+int cuda_trace_sync(cuda_trace_ctx *ctx)
+{
+    if (!ctx)
+        return CUDA_TRACE_ERR_ARG;
+    bool any = false, cancelled = false;
+    float ms_max = 0.0f;
+    for (DeviceState& d : ctx->dev)
+    {
+        CK(cudaSetDevice(d.ordinal));
+        CK(cudaStreamSynchronize(d.stream));
+        if (d.frame_pending)
+        {
+            float ms = 0.0f;
+            CK(cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
+            ms_max = std::max(ms_max, ms);
+            uint32_t flag = 0;
+            CK(cudaMemcpy(&flag, d.d_cancel, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            cancelled = cancelled || flag != 0;
+            d.frame_pending = false;
+            any = true;
+        }
+    }
+    if (any)
+        ctx->last_kernel_ms = ms_max;
+    if (cancelled)
+        return fail(ctx, CUDA_TRACE_ERR_CANCELLED, "frame cancelled");
+    return 0;
+}
+
+int cuda_trace_cancel(cuda_trace_ctx *ctx)
+{
+    if (!ctx)
+        return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::mutex> guard(ctx->cancel_mtx);
+    for (DeviceState& d : ctx->dev)
+    {
+        if (cudaSetDevice(d.ordinal) != cudaSuccess)
+            return CUDA_TRACE_ERR_CUDA;
+        if (cudaMemcpyAsync(d.d_cancel, ctx->pinned_cancel_src, sizeof(uint32_t), cudaMemcpyHostToDevice,
+                            d.side_stream) != cudaSuccess)
+            return CUDA_TRACE_ERR_CUDA;
+    }
+    return 0;
+}
+
+int cuda_trace_read_framebuffer(cuda_trace_ctx *ctx, uint32_t *host_bgra)
+{
+    if (!ctx || !host_bgra)
+        return CUDA_TRACE_ERR_ARG;
+    if (!ctx->d_fb || !ctx->frame_valid)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "read_framebuffer: no frame rendered");
+    DeviceState& d0 = ctx->dev[0];
+    CK(cudaSetDevice(d0.ordinal));
+    const uint32_t w = ctx->fb_w, h = ctx->fb_h;
+    const size_t bytes = (size_t) w * h * sizeof(uint32_t);
+
+    // Pin the caller's buffer once (cached) so the copy is a straight DMA
+    if (ctx->registered_host != host_bgra || ctx->registered_bytes != bytes)
+    {
+        if (ctx->registered_host)
+            cudaHostUnregister(ctx->registered_host);
+        ctx->registered_host = nullptr;
+        if (cudaHostRegister(host_bgra, bytes, cudaHostRegisterDefault) == cudaSuccess)
+        {
+            ctx->registered_host = host_bgra;
+            ctx->registered_bytes = bytes;
+        }
+        else
+            cudaGetLastError(); // already pinned by the caller, or not registrable: plain copy
+    }
+
+    // whole frame covered by a single tile list? then one copy, else one 2-D copy per tile
+    uint64_t covered = 0;
+    for (const auto& t : ctx->tiles)
+        covered += (uint64_t) (t.x1 - t.x0) * (t.y1 - t.y0);
+    if (covered >= (uint64_t) w * h)
+        CK(cudaMemcpyAsync(host_bgra, ctx->d_fb, bytes, cudaMemcpyDeviceToHost, d0.stream));
+    else
+        for (const auto& t : ctx->tiles)
+        {
+            if (t.x1 == t.x0 || t.y1 == t.y0)
+                continue;
+            const size_t o = (size_t) t.y0 * w + t.x0;
+            CK(cudaMemcpy2DAsync(host_bgra + o, (size_t) w * 4, ctx->d_fb + o, (size_t) w * 4,
+                                 (size_t) (t.x1 - t.x0) * 4, t.y1 - t.y0, cudaMemcpyDeviceToHost, d0.stream));
+        }
+    CK(cudaStreamSynchronize(d0.stream));
+    return 0;
+}
+
+int cuda_trace_tiles(cuda_trace_ctx *ctx, const cuda_trace_frame *frame, const cuda_trace_tile_rect *tiles,
+                     uint32_t n_tiles, uint32_t *host_bgra)
+{
+    int rc = cuda_trace_tiles_async(ctx, frame, tiles, n_tiles);
+    if (rc)
+        return rc;
+    if ((rc = cuda_trace_sync(ctx)))
+        return rc;
+    if (host_bgra)
+        return cuda_trace_read_framebuffer(ctx, host_bgra);
+    return 0;
+}
+
+int cuda_trace_last_kernel_ms(cuda_trace_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms)
+        return CUDA_TRACE_ERR_ARG;
+    int rc = cuda_trace_sync(ctx);
+    if (rc)
+        return rc;
+    *ms = ctx->last_kernel_ms;
+    return 0;
+}
+
+int cuda_trace_download_hits(cuda_trace_ctx *ctx, uint32_t *tri_idx, float *t, float *u, float *v)
+{
+    if (!ctx)
+        return CUDA_TRACE_ERR_ARG;
+    int rc = cuda_trace_sync(ctx);
+    if (rc)
+        return rc;
+    if (ctx->hit_count == 0)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "download_hits: last frame was not rendered with CUDA_TRACE_FLAG_KEEP_HITS");
+    CK(cudaSetDevice(ctx->dev[0].ordinal));
+    const size_t bytes = ctx->hit_count * 4;
+    if (tri_idx) CK(cudaMemcpy(tri_idx, ctx->d_hit_tri, bytes, cudaMemcpyDeviceToHost));
+    if (t) CK(cudaMemcpy(t, ctx->d_hit_t, bytes, cudaMemcpyDeviceToHost));
+    if (u) CK(cudaMemcpy(u, ctx->d_hit_u, bytes, cudaMemcpyDeviceToHost));
+    if (v) CK(cudaMemcpy(v, ctx->d_hit_v, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int cuda_trace_intersect_rays(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs,
+                              uint32_t variant, uint32_t *tri_idx, float *t, float *u, float *v)
+{
+    if (!ctx || (n && (!origins || !dirs || !tri_idx || !t || !u || !v)) || variant > 1)
+        return CUDA_TRACE_ERR_ARG;
+    if (!ctx->have_scene)
+        return fail(ctx, CUDA_TRACE_ERR_NO_SCENE, "intersect_rays: upload a scene first");
+    if (n == 0)
+        return 0;
+    DeviceState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.ordinal));
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr, *d_u = nullptr, *d_v = nullptr;
+    uint32_t *d_i = nullptr;
+    CK(cudaMalloc(&d_o, (size_t) n * 12)); CK(cudaMalloc(&d_d, (size_t) n * 12));
+    CK(cudaMalloc(&d_t, (size_t) n * 4)); CK(cudaMalloc(&d_u, (size_t) n * 4));
+    CK(cudaMalloc(&d_v, (size_t) n * 4)); CK(cudaMalloc(&d_i, (size_t) n * 4));
+    CK(cudaMemcpyAsync(d_o, origins, (size_t) n * 12, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d_d, dirs, (size_t) n * 12, cudaMemcpyHostToDevice, d.stream));
+    RayBatchParams p;
+    p.grid = grid_dev(ctx, d);
+    p.n = n; p.origins = d_o; p.dirs = d_d; p.tri = d_i; p.t = d_t; p.u = d_u; p.v = d_v;
+    launch_intersect_rays(p, variant, d.stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(tri_idx, d_i, (size_t) n * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(t, d_t, (size_t) n * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(u, d_u, (size_t) n * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(v, d_v, (size_t) n * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_u); cudaFree(d_v); cudaFree(d_i);
+    return 0;
+}
+
+int cuda_trace_sample_table(cuda_trace_ctx *ctx, uint32_t spp, float *xy)
+{
+    if (!ctx || !xy || spp == 0)
+        return CUDA_TRACE_ERR_ARG;
+    DeviceState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.ordinal));
+    float2 *d_smp = nullptr;
+    CK(cudaMalloc(&d_smp, sizeof(float2) * spp));
+    launch_sample_table(d_smp, spp, d.stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(xy, d_smp, sizeof(float2) * spp, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    CK(cudaFree(d_smp));
+    return 0;
+}
+
+int cuda_trace_get_counters(cuda_trace_ctx *ctx, cuda_trace_counters *out)
+{
+    if (!ctx || !out)
+        return CUDA_TRACE_ERR_ARG;
+    int rc = cuda_trace_sync(ctx);
+    if (rc)
+        return rc;
+    std::memset(out, 0, sizeof(*out));
+    for (DeviceState& d : ctx->dev)
+    {
+        Counters c;
+        CK(cudaSetDevice(d.ordinal));
+        CK(cudaMemcpy(&c, d.d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        out->rays += c.rays; out->cells += c.cells; out->tri_tests += c.tri_tests; out->hits += c.hits;
+    }
+    return 0;
+}
+
+} // extern "C"

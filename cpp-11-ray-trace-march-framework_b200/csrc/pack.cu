@@ -1,0 +1,127 @@
+// K6: scene packing -- Mesh AoS (reference mesh.h:12-24) -> the device layout of rt_device.cuh.
+// Removes the double indirection the reference pays per triangle test (grid.cpp:245-253:
+// cell list -> m_triangles[idx] -> 3 x m_vertices[v].p) and per hit (renderer.cpp:109-115).
+// Compiled with -fmad=false: e1/e2 and the variant-B constants must carry the reference's bits.
+#include "trace_kernels.cuh"
+
+namespace rtm
+{
+
+namespace
+{
+
+__global__ void pack_cell_tris_kernel(const float *__restrict__ vtx, const uint32_t *__restrict__ tri,
+                                      const uint32_t *__restrict__ tri_index, uint64_t num_refs,
+                                      float4 *__restrict__ cell_tris, float4 *__restrict__ cell_tris_b)
+{
+    const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= num_refs)
+        return;
+    const uint32_t ti = tri_index[k];
+    const uint32_t *tr = tri + (size_t) ti * 6;
+    const float *p0 = vtx + (size_t) tr[0] * 6, *p1 = vtx + (size_t) tr[1] * 6, *p2 = vtx + (size_t) tr[2] * 6;
+    const float v0x = p0[0], v0y = p0[1], v0z = p0[2];
+    // triangle.h:39-40 (SUB edge1 = vert1 - vert0, edge2 = vert2 - vert0)
+    const float e1x = p1[0] - v0x, e1y = p1[1] - v0y, e1z = p1[2] - v0z;
+    const float e2x = p2[0] - v0x, e2y = p2[1] - v0y, e2z = p2[2] - v0z;
+    cell_tris[3 * k + 0] = make_float4(v0x, v0y, v0z, __uint_as_float(ti));
+    cell_tris[3 * k + 1] = make_float4(e1x, e1y, e1z, 0.0f);
+    cell_tris[3 * k + 2] = make_float4(e2x, e2y, e2z, 0.0f);
+    // variant B constants: face normal n = Mesh::Triangle::n, d = Dot(n, v0) (triangle.h:205),
+    // ComputeBarycentric's e0 = v2 - v0 (= e2 here), e1 = v1 - v0 (triangle.h:140-149)
+    const float nx = __uint_as_float(tr[3]), ny = __uint_as_float(tr[4]), nz = __uint_as_float(tr[5]);
+    const float d00 = dot_ref(e2x, e2y, e2z, e2x, e2y, e2z);
+    const float d01 = dot_ref(e2x, e2y, e2z, e1x, e1y, e1z);
+    const float d11 = dot_ref(e1x, e1y, e1z, e1x, e1y, e1z);
+    cell_tris_b[2 * k + 0] = make_float4(nx, ny, nz, dot_ref(nx, ny, nz, v0x, v0y, v0z));
+    cell_tris_b[2 * k + 1] = make_float4(d00, d01, d11, 1.0f / (d00 * d11 - d01 * d01));
+}
+
+__global__ void pack_normals_kernel(const float *__restrict__ vtx, const uint32_t *__restrict__ tri,
+                                    uint32_t num_tri, float4 *__restrict__ tri_normals)
+{
+    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= num_tri)
+        return;
+    const uint32_t *tr = tri + (size_t) ti * 6;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+    {
+        const float *n = vtx + (size_t) tr[c] * 6 + 3;
+        tri_normals[3 * (size_t) ti + c] = make_float4(n[0], n[1], n[2], 0.0f);
+    }
+}
+
+__global__ void cell_occupancy_kernel(const uint32_t *__restrict__ cell_start, uint64_t num_cells,
+                                      uint32_t *__restrict__ cell_occ)
+{
+    const uint64_t w = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t first = w * 32;
+    if (first >= num_cells)
+        return;
+    uint32_t bits = 0;
+    const uint32_t n = (uint32_t) min((uint64_t) 32, num_cells - first);
+    uint32_t prev = cell_start[first];
+    for (uint32_t i = 0; i < n; i++)
+    {
+        const uint32_t next = cell_start[first + i + 1];
+        if (next != prev)
+            bits |= 1u << i;
+        prev = next;
+    }
+    cell_occ[w] = bits;
+}
+
+__global__ void narrow_offsets_kernel(const uint64_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = (uint32_t) in[i];
+}
+
+__global__ void widen_offsets_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = in[i];
+}
+
+inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned) ((n + threads - 1) / threads); }
+
+} // namespace
+
+void launch_pack_cell_tris(const float *vtx, const uint32_t *tri, const uint32_t *tri_index, uint64_t num_refs,
+                           float4 *cell_tris, float4 *cell_tris_b, cudaStream_t stream)
+{
+    if (num_refs)
+        pack_cell_tris_kernel<<<blocks_for(num_refs, 256), 256, 0, stream>>>(vtx, tri, tri_index, num_refs,
+                                                                             cell_tris, cell_tris_b);
+}
+
+void launch_pack_normals(const float *vtx, const uint32_t *tri, uint32_t num_tri, float4 *tri_normals,
+                         cudaStream_t stream)
+{
+    if (num_tri)
+        pack_normals_kernel<<<blocks_for(num_tri, 256), 256, 0, stream>>>(vtx, tri, num_tri, tri_normals);
+}
+
+void launch_cell_occupancy(const uint32_t *cell_start, uint64_t num_cells, uint32_t *cell_occ, cudaStream_t stream)
+{
+    const uint64_t words = (num_cells + 31) / 32;
+    if (words)
+        cell_occupancy_kernel<<<blocks_for(words, 256), 256, 0, stream>>>(cell_start, num_cells, cell_occ);
+}
+
+void launch_narrow_offsets(const uint64_t *off64, uint64_t n, uint32_t *off32, cudaStream_t stream)
+{
+    if (n)
+        narrow_offsets_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(off64, n, off32);
+}
+
+void launch_widen_offsets(const uint32_t *off32, uint64_t n, uint64_t *off64, cudaStream_t stream)
+{
+    if (n)
+        widen_offsets_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(off32, n, off64);
+}
+
+} // namespace rtm

@@ -1,0 +1,251 @@
+// K1 trace_tiles, K2 build_sample_table and the ray-batch kernel (sm_100a).
+//
+// K1 supersedes Renderer::RenderTile (reference renderer.cpp:43-136) together with the worker
+// pool that calls it (framebuffer.cpp:59-92): persistent warps pull 8x4-pixel strips of the
+// requested tiles from an atomic counter; the 32 lanes of a warp take the strip's rays in
+// (pixel, sample) order with the SAMPLE index fastest, so a warp works on 32/spp neighbouring
+// pixels at a time and its rays walk (nearly) the same cells.  Ray generation, grid entry,
+// 3D-DDA, ray/triangle tests, shading, the in-order sample average, gamma and BGRA8 packing are
+// all in this one kernel; the only global write is one uint32 per pixel.
+//
+// Compiled with -fmad=false (see rt_device.cuh).
+#include "trace_kernels.cuh"
+
+namespace rtm
+{
+
+namespace
+{
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+template <int VARIANT, bool KEEP_HITS, bool COUNT>
+__device__ __forceinline__ float3 trace_sample(const TraceParams& p, uint32_t px, uint32_t py, uint32_t s,
+                                               const float2 *smp, Counters *cnt)
+{
+    float3 o, d;
+    const float2 off = smp[s];
+    generate_ray(p.cam, px, py, off.x, off.y, o, d);
+    Hit hit;
+    hit.t = hit.u = hit.v = 0.0f;
+    hit.tri = 0xFFFFFFFFu;
+    if (COUNT) cnt->rays++;
+    const bool is_hit = grid_intersect<VARIANT, COUNT>(p.grid, o, d, hit, cnt);
+    if (COUNT && is_hit) cnt->hits++;
+    if (KEEP_HITS)
+    {
+        const size_t k = ((size_t) py * p.width + px) * p.spp + s;
+        p.hit_tri[k] = is_hit ? hit.tri : 0xFFFFFFFFu;
+        if (p.hit_t) p.hit_t[k] = is_hit ? hit.t : 0.0f;
+        if (p.hit_u) p.hit_u[k] = is_hit ? hit.u : 0.0f;
+        if (p.hit_v) p.hit_v[k] = is_hit ? hit.v : 0.0f;
+    }
+    return shade_sample(p.grid, is_hit, hit, py, p.cam.height_f);
+}
+
+template <int VARIANT, bool KEEP_HITS, bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads) trace_tiles_kernel(const __grid_constant__ TraceParams p)
+{
+    extern __shared__ float2 s_smp[]; // sample table (renderer.cpp:49-60), spp entries
+    for (uint32_t i = threadIdx.x; i < p.spp; i += blockDim.x)
+        s_smp[i] = p.smp[i];
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const float spp_f = (float) p.spp;
+    Counters cnt = { 0, 0, 0, 0 };
+
+    for (;;)
+    {
+        // dynamic strip scheduler: one atomic per strip per warp
+        uint32_t fetch = 0;
+        if (lane == 0)
+            fetch = (*(volatile const uint32_t *) p.cancel) ? 0xFFFFFFFFu : atomicAdd(p.strip_counter, 1u);
+        fetch = __shfl_sync(kFull, fetch, 0);
+        const uint64_t strip64 = (uint64_t) fetch * p.shard_world + p.shard_rank;
+        if (fetch == 0xFFFFFFFFu || strip64 >= p.total_strips)
+            break;
+        const uint32_t strip = (uint32_t) strip64;
+
+        // which tile? (upper bound over the per-tile strip prefix)
+        uint32_t lo = 0, hi = p.n_tiles;
+        while (hi - lo > 1)
+        {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&p.tile_strip_prefix[mid]) <= strip) lo = mid; else hi = mid;
+        }
+        const uint4 rect = __ldg(&p.tile_rects[lo]);
+        const uint32_t local = strip - __ldg(&p.tile_strip_prefix[lo]);
+        const uint32_t strips_x = (rect.z - rect.x + kStripW - 1) / kStripW;
+        const uint32_t bx0 = rect.x + (local % strips_x) * kStripW;
+        const uint32_t by0 = rect.y + (local / strips_x) * kStripH;
+        const uint32_t bw = min((uint32_t) kStripW, rect.z - bx0);
+        const uint32_t bh = min((uint32_t) kStripH, rect.w - by0);
+        const uint32_t npix = bw * bh;
+
+        if (p.spp <= 32)
+        {
+            // 32 / spp whole pixels per round; lane = (pixel in round) * spp + sample
+            const uint32_t ppr = 32u / p.spp;
+            const uint32_t pl = lane / p.spp, s = lane - pl * p.spp;
+            for (uint32_t pbase = 0; pbase < npix; pbase += ppr)
+            {
+                const uint32_t pix = pbase + pl;
+                const bool active = pl < ppr && pix < npix;
+                const uint32_t px = bx0 + pix % bw, py = by0 + pix / bw;
+                float3 rgb = make_float3(0.0f, 0.0f, 0.0f);
+                if (active)
+                    rgb = trace_sample<VARIANT, KEEP_HITS, COUNT>(p, px, py, s, s_smp, &cnt);
+                // col += sample, smp = 0..N-1 in order (renderer.cpp:87-122)
+                float3 acc = make_float3(0.0f, 0.0f, 0.0f);
+                const uint32_t base = pl * p.spp;
+                for (uint32_t k = 0; k < p.spp; k++)
+                {
+                    const int src = (int) ((base + k) & 31u);
+                    acc.x += __shfl_sync(kFull, rgb.x, src);
+                    acc.y += __shfl_sync(kFull, rgb.y, src);
+                    acc.z += __shfl_sync(kFull, rgb.z, src);
+                }
+                if (active && s == 0)
+                    p.framebuffer[(size_t) py * p.width + px] = resolve_pixel(acc, spp_f, p.gamma != 0);
+            }
+        }
+        else
+        {
+            // one pixel at a time, 32 samples per round
+            for (uint32_t pix = 0; pix < npix; pix++)
+            {
+                const uint32_t px = bx0 + pix % bw, py = by0 + pix / bw;
+                float3 acc = make_float3(0.0f, 0.0f, 0.0f);
+                for (uint32_t sb = 0; sb < p.spp; sb += 32)
+                {
+                    const uint32_t s = sb + lane;
+                    float3 rgb = make_float3(0.0f, 0.0f, 0.0f);
+                    if (s < p.spp)
+                        rgb = trace_sample<VARIANT, KEEP_HITS, COUNT>(p, px, py, s, s_smp, &cnt);
+                    const uint32_t n = min(32u, p.spp - sb);
+                    for (uint32_t k = 0; k < n; k++)
+                    {
+                        acc.x += __shfl_sync(kFull, rgb.x, (int) k);
+                        acc.y += __shfl_sync(kFull, rgb.y, (int) k);
+                        acc.z += __shfl_sync(kFull, rgb.z, (int) k);
+                    }
+                }
+                if (lane == 0)
+                    p.framebuffer[(size_t) py * p.width + px] = resolve_pixel(acc, spp_f, p.gamma != 0);
+            }
+        }
+    }
+
+    if (COUNT)
+    {
+        atomicAdd(&p.counters->rays, cnt.rays);
+        atomicAdd(&p.counters->cells, cnt.cells);
+        atomicAdd(&p.counters->tri_tests, cnt.tri_tests);
+        atomicAdd(&p.counters->hits, cnt.hits);
+    }
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(128) intersect_rays_kernel(const __grid_constant__ RayBatchParams p)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n)
+        return;
+    const float3 o = make_float3(p.origins[3 * (size_t) i], p.origins[3 * (size_t) i + 1], p.origins[3 * (size_t) i + 2]);
+    const float3 d = make_float3(p.dirs[3 * (size_t) i], p.dirs[3 * (size_t) i + 1], p.dirs[3 * (size_t) i + 2]);
+    Hit hit;
+    hit.t = hit.u = hit.v = 0.0f;
+    hit.tri = 0xFFFFFFFFu;
+    const bool is_hit = grid_intersect<VARIANT, false>(p.grid, o, d, hit, nullptr);
+    p.tri[i] = is_hit ? hit.tri : 0xFFFFFFFFu;
+    p.t[i] = is_hit ? hit.t : 0.0f;
+    p.u[i] = is_hit ? hit.u : 0.0f;
+    p.v[i] = is_hit ? hit.v : 0.0f;
+}
+
+// K2: renderer.cpp:49-60 -> smp[s] = (Hammersley(s,0,N) - 0.5f, Hammersley(s,1,N) - 0.5f) with
+// sampling.h:113-120 / sampling.cpp:194-210 in fp64 (dim 0: double(n)/double(N); dim 1: radical
+// inverse base 2), rounded to fp32 by the store.  No FMA: -fmad=false covers fp64 too.
+__global__ void sample_table_kernel(float2 *smp, uint32_t spp)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= spp)
+        return;
+    const double inv_base = 1.0 / 2.0;
+    double inv_base_i = inv_base, val = 0.0;
+    for (uint32_t n = s; n > 0; n /= 2)
+    {
+        const uint32_t digit = n % 2;
+        val += digit * inv_base_i;
+        inv_base_i *= inv_base;
+    }
+    const double x = (double) s / (double) spp;
+    smp[s] = make_float2((float) (x - 0.5), (float) (val - 0.5));
+}
+
+template <int VARIANT, bool KEEP_HITS, bool COUNT>
+void launch_one(const TraceParams& p, int grid_blocks, cudaStream_t stream)
+{
+    const size_t smem = sizeof(float2) * p.spp;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT><<<grid_blocks, kTraceThreads, smem, stream>>>(p);
+}
+
+template <int VARIANT, bool KEEP_HITS, bool COUNT>
+int occupancy_one()
+{
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT>,
+                                                  kTraceThreads, 1024);
+    return n;
+}
+
+} // namespace
+
+#define RTM_DISPATCH(FN, ...)                                                                    \
+    do {                                                                                         \
+        const int key = (variant ? 4 : 0) | (keep_hits ? 2 : 0) | (count ? 1 : 0);               \
+        switch (key)                                                                             \
+        {                                                                                        \
+            case 0: return FN<0, false, false>(__VA_ARGS__);                                     \
+            case 1: return FN<0, false, true>(__VA_ARGS__);                                      \
+            case 2: return FN<0, true, false>(__VA_ARGS__);                                      \
+            case 3: return FN<0, true, true>(__VA_ARGS__);                                       \
+            case 4: return FN<1, false, false>(__VA_ARGS__);                                     \
+            case 5: return FN<1, false, true>(__VA_ARGS__);                                      \
+            case 6: return FN<1, true, false>(__VA_ARGS__);                                      \
+            default: return FN<1, true, true>(__VA_ARGS__);                                      \
+        }                                                                                        \
+    } while (0)
+
+void launch_trace_tiles(const TraceParams& p, uint32_t variant, bool keep_hits, bool count, int grid_blocks,
+                        cudaStream_t stream)
+{
+    RTM_DISPATCH(launch_one, p, grid_blocks, stream);
+}
+
+int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count)
+{
+    RTM_DISPATCH(occupancy_one);
+}
+
+void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, cudaStream_t stream)
+{
+    const uint32_t blocks = (p.n + 127) / 128;
+    if (blocks == 0)
+        return;
+    if (variant)
+        intersect_rays_kernel<1><<<blocks, 128, 0, stream>>>(p);
+    else
+        intersect_rays_kernel<0><<<blocks, 128, 0, stream>>>(p);
+}
+
+void launch_sample_table(float2 *smp, uint32_t spp, cudaStream_t stream)
+{
+    sample_table_kernel<<<(spp + 127) / 128, 128, 0, stream>>>(smp, spp);
+}
+
+} // namespace rtm

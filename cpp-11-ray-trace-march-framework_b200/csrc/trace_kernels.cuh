@@ -1,0 +1,57 @@
+// Kernel launch interface between api.cu and the .cu files holding the kernels.
+#pragma once
+
+#include "rt_device.cuh"
+
+namespace rtm
+{
+
+constexpr int kStripW = 8;        // a strip is an 8 x 4 pixel block of a tile
+constexpr int kStripH = 4;
+constexpr int kTraceThreads = 128; // 4 warps per CTA, one strip per warp at a time
+
+struct TraceParams
+{
+    GridDev grid;
+    CameraDev cam;
+    uint32_t width, height, spp;
+    uint32_t gamma;
+    const float2 *smp;                 // sample table, spp entries (K2)
+    const uint4 *tile_rects;           // n_tiles x {x0,y0,x1,y1}
+    const uint32_t *tile_strip_prefix; // n_tiles + 1: first strip id of each tile
+    uint32_t n_tiles;
+    uint32_t total_strips;
+    uint32_t shard_rank, shard_world;  // this launch renders strips with id % world == rank
+    uint32_t *strip_counter;           // dynamic strip scheduler (zeroed before launch)
+    const uint32_t *cancel;            // non-zero => stop fetching strips
+    uint32_t *framebuffer;             // width * height, row 0 = y 0 (may be a peer / IPC pointer)
+    uint32_t *hit_tri;                 // optional per-sample records (KEEP_HITS)
+    float *hit_t, *hit_u, *hit_v;
+    Counters *counters;                // optional (COUNT)
+};
+
+struct RayBatchParams
+{
+    GridDev grid;
+    uint32_t n;
+    const float *origins, *dirs;
+    uint32_t *tri;
+    float *t, *u, *v;
+};
+
+void launch_trace_tiles(const TraceParams& p, uint32_t variant, bool keep_hits, bool count, int grid_blocks,
+                        cudaStream_t stream);
+int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count);
+void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, cudaStream_t stream);
+void launch_sample_table(float2 *smp, uint32_t spp, cudaStream_t stream);
+
+// scene packing (pack.cu)
+void launch_pack_cell_tris(const float *vtx, const uint32_t *tri, const uint32_t *tri_index, uint64_t num_refs,
+                           float4 *cell_tris, float4 *cell_tris_b, cudaStream_t stream);
+void launch_pack_normals(const float *vtx, const uint32_t *tri, uint32_t num_tri, float4 *tri_normals,
+                         cudaStream_t stream);
+void launch_cell_occupancy(const uint32_t *cell_start, uint64_t num_cells, uint32_t *cell_occ, cudaStream_t stream);
+void launch_narrow_offsets(const uint64_t *off64, uint64_t n, uint32_t *off32, cudaStream_t stream);
+void launch_widen_offsets(const uint32_t *off32, uint64_t n, uint64_t *off64, cudaStream_t stream);
+
+} // namespace rtm

@@ -1,0 +1,188 @@
+/* cuda_trace.h -- C ABI of the B200 (sm_100a) tile tracer.
+ *
+ * This is the drop-in boundary for the reference's per-tile tracing hot path: everything that
+ * `Framebuffer::WorkerThread` -> `virtual RenderTile(Tile&)` -> `Renderer::RenderTile`
+ * (reference framebuffer.cpp:59-92, framebuffer.h:72-73, renderer.cpp:43-136) does on host
+ * threads is done by these calls on the GPU(s).  Plain C: opaque context, plain pointers and
+ * sizes, no C++/torch types, no exceptions.  Every function returns 0 on success and a non-zero
+ * cuda_trace_status otherwise; cuda_trace_last_error() then describes the failure.  There is no
+ * CPU fallback: without a usable CUDA device cuda_trace_init() fails.
+ *
+ * Ownership: the caller owns every host buffer it passes; the context owns all device memory.
+ * One context must not be used from two threads at once; distinct contexts are independent.
+ *
+ * Which reference interface each entry point replaces is stated at its declaration.
+ */
+#ifndef CUDA_TRACE_H
+#define CUDA_TRACE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cuda_trace_ctx cuda_trace_ctx;
+
+typedef enum cuda_trace_status
+{
+    CUDA_TRACE_OK = 0,
+    CUDA_TRACE_ERR_ARG = 1,       /* bad argument / call order                   */
+    CUDA_TRACE_ERR_CUDA = 2,      /* a CUDA runtime call failed                  */
+    CUDA_TRACE_ERR_NO_DEVICE = 3, /* no (or too few) CUDA devices                */
+    CUDA_TRACE_ERR_NO_SCENE = 4,  /* trace call before a scene + grid were set   */
+    CUDA_TRACE_ERR_CANCELLED = 5  /* cuda_trace_cancel() interrupted the frame   */
+} cuda_trace_status;
+
+#define CUDA_TRACE_MISS 0xFFFFFFFFu
+
+/* Ray/triangle test (reference triangle.h) */
+#define CUDA_TRACE_VARIANT_MT   0u /* IntersectRayTri, non-culling branch (triangle.h:15-107): the live one */
+#define CUDA_TRACE_VARIANT_BARY 1u /* IntersectRayTriBarycentric (triangle.h:210-226)                      */
+
+#define CUDA_TRACE_FLAG_GAMMA     1u /* renderer.cpp:125-131 (#define GAMMA_CORRECTION); on in the reference */
+#define CUDA_TRACE_FLAG_KEEP_HITS 2u /* also record per-sample tri_idx,t,u,v (cuda_trace_download_hits)      */
+
+/* Per-frame inputs of Renderer::RenderTile (renderer.cpp:63-72,91-99): frame size (Framebuffer::
+ * m_width/m_height), sample count (Renderer::m_sample_count), Scene::GetCameraParameters().
+ * fov_xs and aspect are the two constants GenerateRay derives (camera.h:24,41-42); they are
+ * computed ON THE HOST by the caller's toolchain (fov_xs = float(tan(double(DegToRad(fov)/2))))
+ * so that the device never evaluates a transcendental whose rounding could differ. */
+typedef struct cuda_trace_frame
+{
+    uint32_t width;
+    uint32_t height;
+    uint32_t spp;
+    uint32_t variant; /* CUDA_TRACE_VARIANT_* */
+    uint32_t flags;   /* CUDA_TRACE_FLAG_*    */
+    float    fov_xs;
+    float    aspect;
+    float    cam_mat[16]; /* Matrix44f::m_mat in memory order (lin_alg.h:689) */
+} cuda_trace_frame;
+
+/* Framebuffer::Tile::GetPosition (framebuffer.h:41-42): [x0,x1) x [y0,y1) in frame pixels */
+typedef struct cuda_trace_tile_rect
+{
+    uint32_t x0, y0, x1, y1;
+} cuda_trace_tile_rect;
+
+/* Grid description for cuda_trace_upload_grid / cuda_trace_download_grid = the protected state of
+ * the reference's Grid (grid.h:28-39) flattened to CSR in its own cell order
+ * (GridIdx = x + z*dim[0] + y*dim[0]*dim[2], grid.h:41-42). */
+typedef struct cuda_trace_grid_desc
+{
+    uint32_t dim[3];
+    float    aabb_min[3];
+    float    aabb_max[3];
+    float    cell_wdh;
+    float    inv_cell_wdh;
+    uint64_t num_cells; /* dim[0]*dim[1]*dim[2] */
+    uint64_t num_refs;  /* cell_offset[num_cells] */
+} cuda_trace_grid_desc;
+
+/* Work counters of the last frame (optional instrumentation, see cuda_trace_set_counting) */
+typedef struct cuda_trace_counters
+{
+    uint64_t rays, cells, tri_tests, hits;
+} cuda_trace_counters;
+
+/* ---- lifetime -------------------------------------------------------------------------------
+ * Replaces Framebuffer::Framebuffer() choosing hardware_concurrency() worker threads
+ * (framebuffer.cpp:9-13): here the "workers" are n_gpus devices (ordinals 0..n_gpus-1, or the
+ * explicit list).  With n > 1 the scene is replicated and strips are interleaved over the
+ * devices; finished pixels are written into device 0's framebuffer over NVLink peer access. */
+int  cuda_trace_init(int n_gpus, cuda_trace_ctx **out);
+int  cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **out);
+void cuda_trace_destroy(cuda_trace_ctx *ctx);
+const char *cuda_trace_last_error(const cuda_trace_ctx *ctx); /* ctx may be NULL: last init error */
+int  cuda_trace_device_count(void);
+
+/* One-process-per-GPU operation (torchrun): this context renders only the strips
+ * strip_id % world == rank of every frame.  Default rank 0 / world 1. */
+int cuda_trace_set_shard(cuda_trace_ctx *ctx, uint32_t rank, uint32_t world);
+
+/* ---- scene ----------------------------------------------------------------------------------
+ * Replaces Scene::Scene -> Grid::Grid(mesh, grid_res) (scene.cpp:6-10, grid.cpp:12-154) and the
+ * double indirection Grid::Intersect / RenderTile do per triangle (grid.cpp:245-253,
+ * renderer.cpp:109-115): vertices = Mesh::m_vertices (V x {p.xyz, n.xyz}, mesh.h:20-24),
+ * triangles = Mesh::m_triangles (T x {v0,v1,v2, n.xyz}, mesh.h:12-18), both 24-byte records,
+ * passed exactly as they lie in the reference's vectors.  Builds, on every device of the
+ * context, the uniform grid (CSR cell offsets + ascending triangle indices), the cell-major
+ * float4 triangle records and the per-triangle vertex-normal records. */
+int cuda_trace_upload_scene(cuda_trace_ctx *ctx, const float *vertices, uint32_t num_vertices,
+                            const uint32_t *triangles, uint32_t num_triangles, uint32_t grid_res);
+
+/* Same, but with a grid supplied by the caller instead of built on the device (parity harness:
+ * inject the reference's own grid).  cell_offset has desc->num_cells + 1 entries. */
+int cuda_trace_upload_scene_with_grid(cuda_trace_ctx *ctx, const float *vertices, uint32_t num_vertices,
+                                      const uint32_t *triangles, uint32_t num_triangles,
+                                      const cuda_trace_grid_desc *desc, const uint64_t *cell_offset,
+                                      const uint32_t *tri_index);
+
+/* Read back the grid the device holds (desc first; arrays may be NULL to query sizes only) */
+int cuda_trace_download_grid(cuda_trace_ctx *ctx, cuda_trace_grid_desc *desc, uint64_t *cell_offset,
+                             uint32_t *tri_index);
+
+/* ---- tracing --------------------------------------------------------------------------------
+ * cuda_trace_tiles replaces Framebuffer::CreateWorkerThreads + WorkerThread + RenderTile for the
+ * given tiles (framebuffer.cpp:16-27,59-92; renderer.cpp:43-136): it renders every pixel of every
+ * rect and returns after the pixels are in host_bgra (width*height uint32, row 0 = y 0, pixel
+ * value as ToBGRA8 packs it, lin_alg.h:125-132; pixels outside the rects are left untouched).
+ * host_bgra may be NULL (render into the device framebuffer only).
+ * cuda_trace_tiles_async only enqueues the frame; cuda_trace_sync waits for it, and
+ * cuda_trace_read_framebuffer copies the device framebuffer out. */
+int cuda_trace_tiles(cuda_trace_ctx *ctx, const cuda_trace_frame *frame, const cuda_trace_tile_rect *tiles,
+                     uint32_t n_tiles, uint32_t *host_bgra);
+int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *frame,
+                           const cuda_trace_tile_rect *tiles, uint32_t n_tiles);
+int cuda_trace_sync(cuda_trace_ctx *ctx);
+int cuda_trace_read_framebuffer(cuda_trace_ctx *ctx, uint32_t *host_bgra);
+
+/* Framebuffer::m_threads_stop (framebuffer.h:32): ask the running frame to stop early.  Safe to
+ * call from another thread while cuda_trace_tiles / cuda_trace_sync block. */
+int cuda_trace_cancel(cuda_trace_ctx *ctx);
+
+/* Milliseconds the trace kernel of the last completed frame took (CUDA events on its stream,
+ * max over the context's devices) */
+int cuda_trace_last_kernel_ms(cuda_trace_ctx *ctx, float *ms);
+
+/* Per-sample hit records of the last frame rendered with CUDA_TRACE_FLAG_KEEP_HITS, indexed
+ * (y*width + x)*spp + smp: what Grid::Intersect returned for that sample (grid.cpp:159-281);
+ * tri_idx = CUDA_TRACE_MISS (t=u=v=0) on a miss.  Any output pointer may be NULL. */
+int cuda_trace_download_hits(cuda_trace_ctx *ctx, uint32_t *tri_idx, float *t, float *u, float *v);
+
+/* Grid::Intersect (grid.h:16-23, grid.cpp:159-281) for a batch of arbitrary rays: origins / dirs
+ * are n x 3 floats.  tri_idx = CUDA_TRACE_MISS on a miss. */
+int cuda_trace_intersect_rays(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs,
+                              uint32_t variant, uint32_t *tri_idx, float *t, float *u, float *v);
+
+/* The renderer.cpp:49-60 sample table as the device computes it: xy = spp x {x, y} */
+int cuda_trace_sample_table(cuda_trace_ctx *ctx, uint32_t spp, float *xy);
+
+/* Optional instrumentation: count rays / visited cells / triangle tests / hits of the next frames
+ * (slower kernel variant).  cuda_trace_get_counters returns those of the last frame. */
+int cuda_trace_set_counting(cuda_trace_ctx *ctx, int enable);
+int cuda_trace_get_counters(cuda_trace_ctx *ctx, cuda_trace_counters *out);
+
+/* How many kernels this library has launched since cuda_trace_init (all devices) */
+uint64_t cuda_trace_kernel_launches(const cuda_trace_ctx *ctx);
+
+/* ---- multi-process gather (one process per GPU) --------------------------------------------
+ * Rank 0 exports its device framebuffer as a 64-byte CUDA IPC handle; the other ranks import it
+ * and their trace kernels then store finished pixels straight into rank 0's memory over NVLink.
+ * cuda_trace_prepare_framebuffer (re)allocates the device framebuffer for width x height. */
+int cuda_trace_prepare_framebuffer(cuda_trace_ctx *ctx, uint32_t width, uint32_t height);
+int cuda_trace_export_framebuffer(cuda_trace_ctx *ctx, void *handle64);
+int cuda_trace_import_framebuffer(cuda_trace_ctx *ctx, const void *handle64, uint32_t width, uint32_t height);
+
+/* Raw device pointer of the framebuffer the kernels write to (for zero-copy consumers, e.g. a
+ * torch tensor view or CUDA-GL interop) and the CUDA stream handle (cudaStream_t) used on
+ * device 0 */
+void *cuda_trace_framebuffer_device_ptr(cuda_trace_ctx *ctx);
+void *cuda_trace_stream(cuda_trace_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CUDA_TRACE_H */

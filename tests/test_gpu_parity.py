@@ -1,0 +1,194 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+inputs.  Bar: per-sample hit record (tri_idx, t, u, v) bit-exact; 8-bit image bit-exact except
+where IEEE sqrtf differs from glibc powf(x, .5f) (documented: <= 1 LSB)."""
+import numpy as np
+import pytest
+
+from conftest import pkg
+
+pytestmark = pytest.mark.gpu
+
+ALL_SCENES = ["torusknot", "cornell", "room", "table_chair", "head", "room_cat", "water_knot",
+              "griebel_teapot", "killeroo", "dwarf_hand_blob"]
+
+
+def image_diff(a, b):
+    """-> (pixels differing, max per-channel abs difference)"""
+    a8 = a.view(np.uint8).reshape(a.shape + (4,)).astype(np.int16)
+    b8 = b.view(np.uint8).reshape(b.shape + (4,)).astype(np.int16)
+    d = np.abs(a8 - b8)
+    return int((d.max(axis=-1) > 0).sum()), int(d.max())
+
+
+def frame_for(ct, port, sd, w, h, spp, **kw):
+    fov_xs, aspect = port.camera_constants(sd.fov, w, h)
+    return ct.make_frame(w, h, spp, sd.cam16, fov_xs, aspect, **kw)
+
+
+@pytest.mark.parametrize("spp", [1, 2, 3, 4, 5, 16, 32, 33, 64, 256, 1000])
+def test_sample_table(cuda_trace, port, spp):
+    assert np.array_equal(cuda_trace.sample_table(spp).view(np.uint32), port.sample_table(spp).view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ALL_SCENES)
+def test_grid_build_matches_oracle(cuda_trace, port, scene_data, name):
+    sd = scene_data(name)
+    cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
+    g = cuda_trace.download_grid()
+    og = port.scene(sd.vtx, sd.tri, 64).grid()
+    for k in ("dim", "aabb_min", "aabb_max", "cell_wdh", "inv_cell_wdh", "cell_offset", "tri_index"):
+        assert np.array_equal(np.asarray(g[k]), np.asarray(og[k])), k
+
+
+@pytest.mark.parametrize("res", [1, 7, 33, 128])
+def test_grid_build_other_resolutions(cuda_trace, port, scene_data, res):
+    sd = scene_data("killeroo")
+    cuda_trace.upload_scene(sd.vtx, sd.tri, res)
+    g = cuda_trace.download_grid()
+    og = port.scene(sd.vtx, sd.tri, res).grid()
+    for k in ("dim", "cell_wdh", "cell_offset", "tri_index"):
+        assert np.array_equal(np.asarray(g[k]), np.asarray(og[k])), k
+
+
+@pytest.mark.parametrize("name", ALL_SCENES)
+@pytest.mark.parametrize("variant", [0, 1])
+def test_scene_parity_small(cuda_trace, port, scene_data, name, variant):
+    sd = scene_data(name)
+    w, h, spp = 200, 120, 4
+    ps = port.scene(sd.vtx, sd.tri, 64)
+    if variant == 0:
+        cuda_trace.upload_scene(sd.vtx, sd.tri, 64)          # device-built grid
+    else:
+        cuda_trace.upload_scene_with_grid(sd.vtx, sd.tri, ps.grid())  # injected oracle grid
+    f = frame_for(cuda_trace, port, sd, w, h, spp, variant=variant, keep_hits=True)
+    img = cuda_trace.trace_tiles(f)
+    tri, t, u, v = cuda_trace.download_hits(w, h, spp)
+    o = ps.render(sd.cam16, sd.fov, w, h, spp, variant=variant, want_hits=True, want_tuv=True)
+    assert np.array_equal(tri, o["tri"])
+    assert np.array_equal(t.view(np.uint32), o["t"].view(np.uint32))
+    assert np.array_equal(u.view(np.uint32), o["u"].view(np.uint32))
+    assert np.array_equal(v.view(np.uint32), o["v"].view(np.uint32))
+    ndiff, maxd = image_diff(img, o["bgra"])
+    assert maxd <= 1 and ndiff <= 0.001 * w * h, (ndiff, maxd)
+
+
+@pytest.mark.parametrize("spp", [1, 2, 3, 5, 16, 32, 33, 70])
+def test_sample_counts(cuda_trace, port, scene_data, spp):
+    sd = scene_data("cornell")
+    w, h = 67, 45  # not multiples of the 8x4 strip
+    cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
+    f = frame_for(cuda_trace, port, sd, w, h, spp, keep_hits=True)
+    img = cuda_trace.trace_tiles(f)
+    tri, t, u, v = cuda_trace.download_hits(w, h, spp)
+    o = port.scene(sd.vtx, sd.tri, 64).render(sd.cam16, sd.fov, w, h, spp, want_hits=True)
+    assert np.array_equal(tri, o["tri"])
+    ndiff, maxd = image_diff(img, o["bgra"])
+    assert maxd <= 1 and ndiff <= max(1, 0.001 * w * h), (ndiff, maxd)
+
+
+def test_ragged_tiles_and_untouched_pixels(cuda_trace, port, scene_data):
+    sd = scene_data("cornell")
+    w, h, spp = 131, 77, 4
+    cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
+    f = frame_for(cuda_trace, port, sd, w, h, spp)
+    rects = [(0, 0, 1, 1), (5, 3, 5, 9), (7, 7, 7, 7), (10, 10, 29, 13), (100, 50, 131, 77), (40, 20, 49, 55)]
+    out = np.full((h, w), 0xDEADBEEF, np.uint32)
+    cuda_trace.trace_tiles(f, rects, out=out)
+    o = port.scene(sd.vtx, sd.tri, 64).render(sd.cam16, sd.fov, w, h, spp)["bgra"]
+    mask = np.zeros((h, w), bool)
+    for x0, y0, x1, y1 in rects:
+        mask[y0:y1, x0:x1] = True
+    assert (out[~mask] == 0xDEADBEEF).all()
+    ndiff, maxd = image_diff(out[mask], o[mask])
+    assert maxd <= 1 and ndiff <= 2
+    # empty tile list is legal and renders nothing
+    out2 = np.full((h, w), 7, np.uint32)
+    cuda_trace.trace_tiles(f, [], out=out2)
+    assert (out2 == 7).all()
+
+
+def test_no_gamma_flag(cuda_trace, port, scene_data):
+    sd = scene_data("cornell")
+    w, h, spp = 64, 64, 2
+    cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
+    f = frame_for(cuda_trace, port, sd, w, h, spp, gamma=False)
+    img = cuda_trace.trace_tiles(f)
+    o = port.scene(sd.vtx, sd.tri, 64).render(sd.cam16, sd.fov, w, h, spp, gamma=False)["bgra"]
+    assert np.array_equal(img, o)  # without the powf/sqrtf difference the image is bit-exact
+
+
+def test_arbitrary_rays(cuda_trace, port, scene_data):
+    """Grid::Intersect on rays the camera never produces: axis-aligned directions (zero
+    components -> +-inf slabs), origins inside / on / behind the box, unnormalised directions."""
+    sd = scene_data("cornell")
+    cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
+    ps = port.scene(sd.vtx, sd.tri, 64)
+    g = ps.grid()
+    rs = np.random.RandomState(7)
+    n = 20000
+    o = rs.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    d = rs.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    # axis aligned and planar directions
+    d[:3000, 0] = 0.0
+    d[1000:4000, 1] = 0.0
+    d[4000:4600] = np.eye(3, dtype=np.float32)[rs.randint(0, 3, 600)] * rs.choice([-1, 1], (600, 1))
+    d[4600:4700, 2] = -0.0
+    # origins inside the box, exactly on its faces, and unnormalised directions
+    o[5000:9000] = rs.uniform(-0.45, 0.45, (4000, 3)).astype(np.float32)
+    o[9000:9300, 0] = g["aabb_min"][0]
+    o[9300:9600, 1] = g["aabb_max"][1]
+    d[9600:10000] *= rs.uniform(0.1, 10, (400, 1)).astype(np.float32)
+    keep = np.abs(d).sum(axis=1) > 0
+    o, d = o[keep], d[keep]
+    for variant in (0, 1):
+        tri, t, u, v = cuda_trace.intersect_rays(o, d, variant)
+        otri, ot, ou, ov = ps.intersect_rays(o, d, variant)
+        assert np.array_equal(tri, otri)
+        assert np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+        assert np.array_equal(u.view(np.uint32), ou.view(np.uint32))
+        assert np.array_equal(v.view(np.uint32), ov.view(np.uint32))
+        assert (tri != 0xFFFFFFFF).sum() > 1000
+
+
+def test_counters_match_oracle(cuda_trace, port, scene_data):
+    sd = scene_data("killeroo")
+    w, h, spp = 160, 90, 4
+    cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
+    cuda_trace.set_counting(True)
+    try:
+        f = frame_for(cuda_trace, port, sd, w, h, spp)
+        cuda_trace.trace_tiles(f)
+        c = cuda_trace.get_counters()
+    finally:
+        cuda_trace.set_counting(False)
+    oc = port.scene(sd.vtx, sd.tri, 64).render(sd.cam16, sd.fov, w, h, spp)["counters"]
+    for k in ("rays", "cells", "tri_tests", "hits"):
+        assert c[k] == oc[k], k
+
+
+def test_errors(cuda_trace, scene_data):
+    capi = pkg("capi")
+    ct = capi.CudaTrace(1)
+    try:
+        f = ct.make_frame(16, 16, 1, np.eye(4, dtype=np.float32).reshape(16), 0.5, 1.0)
+        with pytest.raises(capi.CudaTraceError) as e:
+            ct.trace_tiles(f)
+        assert e.value.code == 4  # CUDA_TRACE_ERR_NO_SCENE
+        sd = scene_data("cornell")
+        bad = sd.tri.copy()
+        bad[0, 0] = len(sd.vtx)
+        with pytest.raises(capi.CudaTraceError):
+            ct.upload_scene(sd.vtx, bad, 64)
+        with pytest.raises(capi.CudaTraceError):
+            ct.upload_scene(sd.vtx, sd.tri, 0)
+        ct.upload_scene(sd.vtx, sd.tri, 64)
+        with pytest.raises(capi.CudaTraceError):
+            ct.trace_tiles(f, [(0, 0, 17, 16)])  # tile outside the frame
+        f0 = ct.make_frame(16, 16, 0, np.eye(4, dtype=np.float32).reshape(16), 0.5, 1.0)
+        with pytest.raises(capi.CudaTraceError):
+            ct.trace_tiles(f0)
+    finally:
+        ct.close()
+    with pytest.raises(capi.CudaTraceError):
+        capi.CudaTrace(devices=[99])
