@@ -52,8 +52,34 @@ def build_cuda(force=False, verbose=False):
     return LIB_CUDA
 
 
+HOST = os.path.join(PKG, "host")
+LIB_HOST = os.path.join(PKG, "librtm_host.so")
+CXX = "g++"
+# -ffp-contract=off: mesh transforms must round like the reference's (no FMA), see host/lin_alg.h
+CXX_FLAGS = ["-std=c++11", "-O2", "-g", "-fPIC", "-pthread", "-Wall", "-Wextra", "-ffp-contract=off"]
+HOST_SOURCES = ["mesh.cpp", "grid.cpp", "framebuffer.cpp", "renderer.cpp", "bmp_writer.cpp", "trace.cpp", "capi.cpp"]
+
+
+def build_host(force=False, verbose=False):
+    """librtm_host.so: the C++ mirror of the reference's Mesh/Scene/Grid/Framebuffer/Renderer API
+    (host/*.cpp) + flat C wrappers; links against libcuda_trace.so next to it."""
+    srcs = [os.path.join(HOST, s) for s in HOST_SOURCES]
+    deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")]
+    deps += [os.path.join(ROOT, "include", "cuda_trace.h"), LIB_CUDA]
+    if not force and not _newer(LIB_HOST, deps):
+        return LIB_HOST
+    cmd = [CXX] + CXX_FLAGS + ["-shared", "-o", LIB_HOST] + srcs + [
+        "-L" + PKG, "-lcuda_trace", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("g++ failed: " + " ".join(cmd))
+    return LIB_HOST
+
+
 def build_all(force=False, verbose=False):
-    return [build_cuda(force, verbose)]
+    return [build_cuda(force, verbose), build_host(force, verbose)]
 
 
 if __name__ == "__main__":

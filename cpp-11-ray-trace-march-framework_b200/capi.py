@@ -65,6 +65,7 @@ SYMBOLS = {
     "cuda_trace_sample_table": (C.c_int, [C.c_void_p, C.c_uint32, _F32P]),
     "cuda_trace_set_counting": (C.c_int, [C.c_void_p, C.c_int]),
     "cuda_trace_get_counters": (C.c_int, [C.c_void_p, C.POINTER(CountersC)]),
+    "cuda_trace_flush_l2": (C.c_int, [C.c_void_p]),
     "cuda_trace_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "cuda_trace_prepare_framebuffer": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "cuda_trace_export_framebuffer": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -262,6 +263,9 @@ class CudaTrace:
         c = CountersC()
         self._ck(self.lib.cuda_trace_get_counters(self.h, C.byref(c)))
         return dict(rays=int(c.rays), cells=int(c.cells), tri_tests=int(c.tri_tests), hits=int(c.hits))
+
+    def flush_l2(self):
+        self._ck(self.lib.cuda_trace_flush_l2(self.h))
 
     def kernel_launches(self):
         return int(self.lib.cuda_trace_kernel_launches(self.h))

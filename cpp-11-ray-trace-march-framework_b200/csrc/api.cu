@@ -34,6 +34,7 @@ struct DeviceState
     float *d_vtx = nullptr;
     uint32_t *d_tri = nullptr;
     uint32_t *d_cell_start = nullptr, *d_cell_occ = nullptr, *d_tri_index = nullptr;
+    uint32_t *d_pcell_start = nullptr, *d_pcell_occ = nullptr; // padded grid (rt_device.cuh)
     float4 *d_cell_tris = nullptr, *d_cell_tris_b = nullptr, *d_tri_normals = nullptr;
 
     // frame
@@ -45,6 +46,7 @@ struct DeviceState
     uint32_t *d_strip_counter = nullptr;
     uint32_t *d_cancel = nullptr;
     Counters *d_counters = nullptr;
+    void *d_l2_scratch = nullptr;
     bool frame_pending = false;
 };
 
@@ -62,6 +64,7 @@ struct cuda_trace_ctx
 
     uint32_t shard_rank = 0, shard_world = 1;
     bool counting = false;
+    bool occ_in_smem = true;
     std::atomic<uint64_t> launches{0};
 
     // framebuffer (device 0, or an imported IPC mapping of another process' framebuffer)
@@ -110,6 +113,8 @@ void free_scene(DeviceState& d)
     cudaSetDevice(d.ordinal);
     cudaFree(d.d_vtx); cudaFree(d.d_tri); cudaFree(d.d_cell_start); cudaFree(d.d_cell_occ);
     cudaFree(d.d_tri_index); cudaFree(d.d_cell_tris); cudaFree(d.d_cell_tris_b); cudaFree(d.d_tri_normals);
+    cudaFree(d.d_pcell_start); cudaFree(d.d_pcell_occ);
+    d.d_pcell_start = nullptr; d.d_pcell_occ = nullptr;
     d.d_vtx = nullptr; d.d_tri = nullptr; d.d_cell_start = nullptr; d.d_cell_occ = nullptr;
     d.d_tri_index = nullptr; d.d_cell_tris = nullptr; d.d_cell_tris_b = nullptr; d.d_tri_normals = nullptr;
 }
@@ -127,6 +132,8 @@ GridDev grid_dev(const cuda_trace_ctx *ctx, const DeviceState& d)
     g.inv_cell_wdh = ctx->desc.inv_cell_wdh;
     g.cell_start = d.d_cell_start;
     g.cell_occ = d.d_cell_occ;
+    g.pcell_start = d.d_pcell_start;
+    g.pcell_occ = d.d_pcell_occ;
     g.cell_tris = d.d_cell_tris;
     g.cell_tris_b = d.d_cell_tris_b;
     g.tri_normals = d.d_tri_normals;
@@ -137,11 +144,18 @@ GridDev grid_dev(const cuda_trace_ctx *ctx, const DeviceState& d)
 int finish_scene_on_device(cuda_trace_ctx *ctx, DeviceState& d)
 {
     const uint64_t cells = ctx->desc.num_cells, refs = ctx->desc.num_refs;
+    const uint64_t pcells = (uint64_t) (ctx->desc.dim[0] + 2) * (ctx->desc.dim[1] + 2) * (ctx->desc.dim[2] + 2);
+    if (pcells >= (1ull << 31))
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "grid too large: padded cell count must stay below 2^31");
     CK(cudaMalloc(&d.d_cell_occ, ((cells + 31) / 32) * sizeof(uint32_t)));
+    CK(cudaMalloc(&d.d_pcell_start, (pcells + 1) * sizeof(uint32_t)));
+    CK(cudaMalloc(&d.d_pcell_occ, ((pcells + 31) / 32) * sizeof(uint32_t)));
     CK(cudaMalloc(&d.d_cell_tris, std::max<uint64_t>(refs, 1) * 3 * sizeof(float4)));
     CK(cudaMalloc(&d.d_cell_tris_b, std::max<uint64_t>(refs, 1) * 2 * sizeof(float4)));
     CK(cudaMalloc(&d.d_tri_normals, (size_t) ctx->num_tri * 3 * sizeof(float4)));
     launch_cell_occupancy(d.d_cell_start, cells, d.d_cell_occ, d.stream);
+    launch_pad_grid(d.d_cell_start, ctx->desc.dim, d.d_pcell_start, d.d_pcell_occ, d.stream);
+    ctx->launches += 2;
     launch_pack_cell_tris(d.d_vtx, d.d_tri, d.d_tri_index, refs, d.d_cell_tris, d.d_cell_tris_b, d.stream);
     launch_pack_normals(d.d_vtx, d.d_tri, ctx->num_tri, d.d_tri_normals, d.stream);
     ctx->launches += 2 + (refs ? 1 : 0);
@@ -307,7 +321,7 @@ void cuda_trace_destroy(cuda_trace_ctx *ctx)
     {
         free_scene(d);
         cudaFree(d.d_smp); cudaFree(d.d_tile_rects); cudaFree(d.d_tile_prefix); cudaFree(d.d_strip_counter);
-        cudaFree(d.d_cancel); cudaFree(d.d_counters);
+        cudaFree(d.d_cancel); cudaFree(d.d_counters); cudaFree(d.d_l2_scratch);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
         if (d.stream) cudaStreamDestroy(d.stream);
@@ -640,6 +654,14 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const
         p.spp = f->spp;
         p.gamma = (f->flags & CUDA_TRACE_FLAG_GAMMA) ? 1u : 0u;
         p.smp = d.d_smp;
+        {
+            // stage the padded occupancy bitmap in shared memory when it is small (res-64 grids: <= 36 KB)
+            const uint64_t pcells = (uint64_t) (ctx->desc.dim[0] + 2) * (ctx->desc.dim[1] + 2) * (ctx->desc.dim[2] + 2);
+            const uint64_t words = (pcells + 31) / 32;
+            // (tiny frames: the per-CTA copy would cost more than it saves)
+            const bool big_frame = (uint64_t) f->width * f->height * f->spp >= (4u << 20);
+            p.occ_smem_words = (ctx->occ_in_smem && big_frame && words * 4 <= 40 * 1024) ? (uint32_t) words : 0u;
+        }
         p.tile_rects = d.d_tile_rects;
         p.tile_strip_prefix = d.d_tile_prefix;
         p.n_tiles = n_tiles;
@@ -656,7 +678,9 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const
         p.hit_v = keep_hits ? ctx->d_hit_v : nullptr;
         p.counters = d.d_counters;
 
-        const int per_sm = std::max(1, trace_tiles_max_blocks_per_sm(f->variant, keep_hits, ctx->counting));
+        const int per_sm = std::max(1, trace_tiles_max_blocks_per_sm(f->variant, keep_hits, ctx->counting,
+                                                                       sizeof(float2) * f->spp + sizeof(uint32_t) * p.occ_smem_words,
+                                                                       p.occ_smem_words != 0));
         const uint64_t my_strips = (total + p.shard_world - 1) / p.shard_world;
         const uint64_t want = (my_strips + (kTraceThreads / 32) - 1) / (kTraceThreads / 32);
         const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) d.sm_count * per_sm, want));
@@ -852,6 +876,21 @@ int cuda_trace_sample_table(cuda_trace_ctx *ctx, uint32_t spp, float *xy)
     CK(cudaMemcpyAsync(xy, d_smp, sizeof(float2) * spp, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaStreamSynchronize(d.stream));
     CK(cudaFree(d_smp));
+    return 0;
+}
+
+int cuda_trace_flush_l2(cuda_trace_ctx *ctx)
+{
+    if (!ctx)
+        return CUDA_TRACE_ERR_ARG;
+    const size_t bytes = 256u << 20;
+    for (DeviceState& d : ctx->dev)
+    {
+        CK(cudaSetDevice(d.ordinal));
+        if (!d.d_l2_scratch)
+            CK(cudaMalloc(&d.d_l2_scratch, bytes));
+        CK(cudaMemsetAsync(d.d_l2_scratch, 0xA5, bytes, d.stream));
+    }
     return 0;
 }
 

@@ -72,6 +72,63 @@ __global__ void cell_occupancy_kernel(const uint32_t *__restrict__ cell_start, u
     cell_occ[w] = bits;
 }
 
+// Padded grid (see rt_device.cuh): padded cell q = X + Z*pdx + Y*pdx*pdz with X in [0, dx+2) etc.
+// Interior cells keep their relative order, so the padded CSR offset of q is the unpadded offset
+// of the first interior cell at or after q.
+__device__ __forceinline__ uint32_t interior_cells_before(uint32_t X, uint32_t Y, uint32_t Z, uint32_t dx,
+                                                          uint32_t dy, uint32_t dz)
+{
+    const uint32_t ys = min(Y > 0 ? Y - 1 : 0u, dy);
+    uint32_t r = ys * dx * dz;
+    if (Y >= 1 && Y <= dy)
+    {
+        const uint32_t zs = min(Z > 0 ? Z - 1 : 0u, dz);
+        r += zs * dx;
+        if (Z >= 1 && Z <= dz)
+            r += min(X > 0 ? X - 1 : 0u, dx);
+    }
+    return r;
+}
+
+__global__ void pad_cell_start_kernel(const uint32_t *__restrict__ cell_start, uint32_t dx, uint32_t dy, uint32_t dz,
+                                      uint32_t *__restrict__ pcell_start)
+{
+    const uint32_t pdx = dx + 2, pdy = dy + 2, pdz = dz + 2;
+    const uint64_t pcells = (uint64_t) pdx * pdy * pdz;
+    const uint64_t q = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > pcells)
+        return;
+    if (q == pcells)
+    {
+        pcell_start[q] = cell_start[(uint64_t) dx * dy * dz];
+        return;
+    }
+    const uint32_t X = (uint32_t) (q % pdx), Z = (uint32_t) ((q / pdx) % pdz), Y = (uint32_t) (q / ((uint64_t) pdx * pdz));
+    pcell_start[q] = cell_start[interior_cells_before(X, Y, Z, dx, dy, dz)];
+}
+
+__global__ void pad_cell_occ_kernel(const uint32_t *__restrict__ pcell_start, uint32_t dx, uint32_t dy, uint32_t dz,
+                                    uint32_t *__restrict__ pcell_occ)
+{
+    const uint32_t pdx = dx + 2, pdy = dy + 2, pdz = dz + 2;
+    const uint64_t pcells = (uint64_t) pdx * pdy * pdz;
+    const uint64_t w = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t first = w * 32;
+    if (first >= pcells)
+        return;
+    uint32_t bits = 0;
+    const uint32_t n = (uint32_t) min((uint64_t) 32, pcells - first);
+    for (uint32_t i = 0; i < n; i++)
+    {
+        const uint64_t q = first + i;
+        const uint32_t X = (uint32_t) (q % pdx), Z = (uint32_t) ((q / pdx) % pdz), Y = (uint32_t) (q / ((uint64_t) pdx * pdz));
+        const bool border = X == 0 || X == pdx - 1 || Y == 0 || Y == pdy - 1 || Z == 0 || Z == pdz - 1;
+        if (border || pcell_start[q] != pcell_start[q + 1])
+            bits |= 1u << i;
+    }
+    pcell_occ[w] = bits;
+}
+
 __global__ void narrow_offsets_kernel(const uint64_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out)
 {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,6 +167,14 @@ void launch_cell_occupancy(const uint32_t *cell_start, uint64_t num_cells, uint3
     const uint64_t words = (num_cells + 31) / 32;
     if (words)
         cell_occupancy_kernel<<<blocks_for(words, 256), 256, 0, stream>>>(cell_start, num_cells, cell_occ);
+}
+
+void launch_pad_grid(const uint32_t *cell_start, const uint32_t dim[3], uint32_t *pcell_start, uint32_t *pcell_occ,
+                     cudaStream_t stream)
+{
+    const uint64_t pcells = (uint64_t) (dim[0] + 2) * (dim[1] + 2) * (dim[2] + 2);
+    pad_cell_start_kernel<<<blocks_for(pcells + 1, 256), 256, 0, stream>>>(cell_start, dim[0], dim[1], dim[2], pcell_start);
+    pad_cell_occ_kernel<<<blocks_for((pcells + 31) / 32, 256), 256, 0, stream>>>(pcell_start, dim[0], dim[1], dim[2], pcell_occ);
 }
 
 void launch_narrow_offsets(const uint64_t *off64, uint64_t n, uint32_t *off32, cudaStream_t stream)

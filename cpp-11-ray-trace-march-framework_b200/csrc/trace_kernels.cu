@@ -10,6 +10,7 @@
 //
 // Compiled with -fmad=false (see rt_device.cuh).
 #include "trace_kernels.cuh"
+#include "warp_trace.cuh"
 
 namespace rtm
 {
@@ -19,20 +20,21 @@ namespace
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
-template <int VARIANT, bool KEEP_HITS, bool COUNT>
-__device__ __forceinline__ float3 trace_sample(const TraceParams& p, uint32_t px, uint32_t py, uint32_t s,
-                                               const float2 *smp, Counters *cnt)
+// One sample per lane; ALL lanes of the warp call this together (valid == false: no ray)
+template <int VARIANT, bool KEEP_HITS, bool COUNT, bool OCC_SMEM>
+__device__ __forceinline__ float3 trace_sample(const TraceParams& p, const uint32_t *s_occ, bool valid,
+                                               uint32_t px, uint32_t py, uint32_t s, const float2 *smp, Counters *cnt)
 {
     float3 o, d;
-    const float2 off = smp[s];
+    const float2 off = smp[valid ? s : 0];
     generate_ray(p.cam, px, py, off.x, off.y, o, d);
     Hit hit;
     hit.t = hit.u = hit.v = 0.0f;
     hit.tri = 0xFFFFFFFFu;
-    if (COUNT) cnt->rays++;
-    const bool is_hit = grid_intersect<VARIANT, COUNT>(p.grid, o, d, hit, cnt);
+    if (COUNT && valid) cnt->rays++;
+    const bool is_hit = warp_grid_intersect<VARIANT, COUNT, OCC_SMEM>(p.grid, s_occ, o, d, valid, hit, cnt);
     if (COUNT && is_hit) cnt->hits++;
-    if (KEEP_HITS)
+    if (KEEP_HITS && valid)
     {
         const size_t k = ((size_t) py * p.width + px) * p.spp + s;
         p.hit_tri[k] = is_hit ? hit.tri : 0xFFFFFFFFu;
@@ -40,13 +42,23 @@ __device__ __forceinline__ float3 trace_sample(const TraceParams& p, uint32_t px
         if (p.hit_u) p.hit_u[k] = is_hit ? hit.u : 0.0f;
         if (p.hit_v) p.hit_v[k] = is_hit ? hit.v : 0.0f;
     }
-    return shade_sample(p.grid, is_hit, hit, py, p.cam.height_f);
+    float3 rgb = make_float3(0.0f, 0.0f, 0.0f);
+    if (valid)
+        rgb = shade_sample(p.grid, is_hit, hit, py, p.cam.height_f);
+    return rgb;
 }
 
-template <int VARIANT, bool KEEP_HITS, bool COUNT>
+template <int VARIANT, bool KEEP_HITS, bool COUNT, bool OCC_SMEM>
 __global__ void __launch_bounds__(kTraceThreads) trace_tiles_kernel(const __grid_constant__ TraceParams p)
 {
-    extern __shared__ float2 s_smp[]; // sample table (renderer.cpp:49-60), spp entries
+    // shared memory: [sample table (renderer.cpp:49-60), spp x float2]
+    //                [padded occupancy bits (p.occ_smem_words; only when OCC_SMEM)]
+    extern __shared__ float2 s_mem[];
+    float2 *s_smp = s_mem;
+    uint32_t *s_occ = reinterpret_cast<uint32_t *>(s_mem + p.spp);
+    if (OCC_SMEM)
+        for (uint32_t i = threadIdx.x; i < p.occ_smem_words; i += blockDim.x)
+            s_occ[i] = __ldg(&p.grid.pcell_occ[i]);
     for (uint32_t i = threadIdx.x; i < p.spp; i += blockDim.x)
         s_smp[i] = p.smp[i];
     __syncthreads();
@@ -82,20 +94,26 @@ __global__ void __launch_bounds__(kTraceThreads) trace_tiles_kernel(const __grid
         const uint32_t bw = min((uint32_t) kStripW, rect.z - bx0);
         const uint32_t bh = min((uint32_t) kStripH, rect.w - by0);
         const uint32_t npix = bw * bh;
+        (void) npix;
 
         if (p.spp <= 32)
         {
-            // 32 / spp whole pixels per round; lane = (pixel in round) * spp + sample
+            // 32 / spp whole pixels per round; lane = (pixel in round) * spp + sample.  The 32
+            // pixel slots of the 8x4 strip are visited in 2x2-quad (Morton) order, so the pixels
+            // of one round form a compact block (spp 16: 2x1, spp 4: 4x2, spp 1: 8x4) whose rays
+            // walk nearly the same cells.
             const uint32_t ppr = 32u / p.spp;
             const uint32_t pl = lane / p.spp, s = lane - pl * p.spp;
-            for (uint32_t pbase = 0; pbase < npix; pbase += ppr)
+            for (uint32_t pbase = 0; pbase < 32u; pbase += ppr)
             {
-                const uint32_t pix = pbase + pl;
-                const bool active = pl < ppr && pix < npix;
-                const uint32_t px = bx0 + pix % bw, py = by0 + pix / bw;
-                float3 rgb = make_float3(0.0f, 0.0f, 0.0f);
-                if (active)
-                    rgb = trace_sample<VARIANT, KEEP_HITS, COUNT>(p, px, py, s, s_smp, &cnt);
+                const uint32_t slot = pbase + pl;
+                const uint32_t ox = (slot & 1u) | ((slot >> 1) & 2u) | ((slot >> 2) & 4u);
+                const uint32_t oy = ((slot >> 1) & 1u) | ((slot >> 2) & 2u);
+                const bool active = pl < ppr && slot < 32u && ox < bw && oy < bh;
+                if (!__any_sync(kFull, active))
+                    continue;
+                const uint32_t px = bx0 + ox, py = by0 + oy;
+                const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_SMEM>(p, s_occ, active, px, py, s, s_smp, &cnt);
                 // col += sample, smp = 0..N-1 in order (renderer.cpp:87-122)
                 float3 acc = make_float3(0.0f, 0.0f, 0.0f);
                 const uint32_t base = pl * p.spp;
@@ -120,9 +138,7 @@ __global__ void __launch_bounds__(kTraceThreads) trace_tiles_kernel(const __grid
                 for (uint32_t sb = 0; sb < p.spp; sb += 32)
                 {
                     const uint32_t s = sb + lane;
-                    float3 rgb = make_float3(0.0f, 0.0f, 0.0f);
-                    if (s < p.spp)
-                        rgb = trace_sample<VARIANT, KEEP_HITS, COUNT>(p, px, py, s, s_smp, &cnt);
+                    const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_SMEM>(p, s_occ, s < p.spp, px, py, s, s_smp, &cnt);
                     const uint32_t n = min(32u, p.spp - sb);
                     for (uint32_t k = 0; k < n; k++)
                     {
@@ -187,19 +203,43 @@ __global__ void sample_table_kernel(float2 *smp, uint32_t spp)
 template <int VARIANT, bool KEEP_HITS, bool COUNT>
 void launch_one(const TraceParams& p, int grid_blocks, cudaStream_t stream)
 {
-    const size_t smem = sizeof(float2) * p.spp;
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT><<<grid_blocks, kTraceThreads, smem, stream>>>(p);
+    const size_t smem = sizeof(float2) * p.spp + sizeof(uint32_t) * p.occ_smem_words;
+    if (p.occ_smem_words)
+    {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, true><<<grid_blocks, kTraceThreads, smem, stream>>>(p);
+    }
+    else
+    {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, false><<<grid_blocks, kTraceThreads, smem, stream>>>(p);
+    }
 }
 
 template <int VARIANT, bool KEEP_HITS, bool COUNT>
-int occupancy_one()
+int occupancy_one(size_t smem, bool occ_smem)
 {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT>,
-                                                  kTraceThreads, 1024);
+    if (occ_smem)
+    {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, true>,
+                                                      kTraceThreads, smem);
+    }
+    else
+    {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, false>,
+                                                      kTraceThreads, smem);
+    }
     return n;
 }
 
@@ -227,9 +267,9 @@ void launch_trace_tiles(const TraceParams& p, uint32_t variant, bool keep_hits, 
     RTM_DISPATCH(launch_one, p, grid_blocks, stream);
 }
 
-int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count)
+int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count, size_t smem_bytes, bool occ_smem)
 {
-    RTM_DISPATCH(occupancy_one);
+    RTM_DISPATCH(occupancy_one, smem_bytes, occ_smem);
 }
 
 void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, cudaStream_t stream)

@@ -8,7 +8,7 @@ namespace rtm
 
 constexpr int kStripW = 8;        // a strip is an 8 x 4 pixel block of a tile
 constexpr int kStripH = 4;
-constexpr int kTraceThreads = 128; // 4 warps per CTA, one strip per warp at a time
+constexpr int kTraceThreads = 256; // 8 warps per CTA, one strip per warp at a time
 
 struct TraceParams
 {
@@ -17,6 +17,7 @@ struct TraceParams
     uint32_t width, height, spp;
     uint32_t gamma;
     const float2 *smp;                 // sample table, spp entries (K2)
+    uint32_t occ_smem_words;           // padded occupancy words staged in shared memory (0: read through L1)
     const uint4 *tile_rects;           // n_tiles x {x0,y0,x1,y1}
     const uint32_t *tile_strip_prefix; // n_tiles + 1: first strip id of each tile
     uint32_t n_tiles;
@@ -41,7 +42,7 @@ struct RayBatchParams
 
 void launch_trace_tiles(const TraceParams& p, uint32_t variant, bool keep_hits, bool count, int grid_blocks,
                         cudaStream_t stream);
-int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count);
+int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count, size_t smem_bytes, bool occ_smem);
 void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, cudaStream_t stream);
 void launch_sample_table(float2 *smp, uint32_t spp, cudaStream_t stream);
 
@@ -51,6 +52,8 @@ void launch_pack_cell_tris(const float *vtx, const uint32_t *tri, const uint32_t
 void launch_pack_normals(const float *vtx, const uint32_t *tri, uint32_t num_tri, float4 *tri_normals,
                          cudaStream_t stream);
 void launch_cell_occupancy(const uint32_t *cell_start, uint64_t num_cells, uint32_t *cell_occ, cudaStream_t stream);
+void launch_pad_grid(const uint32_t *cell_start, const uint32_t dim[3], uint32_t *pcell_start, uint32_t *pcell_occ,
+                     cudaStream_t stream); // 2 kernels
 void launch_narrow_offsets(const uint64_t *off64, uint64_t n, uint32_t *off32, cudaStream_t stream);
 void launch_widen_offsets(const uint32_t *off32, uint64_t n, uint64_t *off64, cudaStream_t stream);
 

@@ -1,0 +1,71 @@
+#include "renderer.h"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/cuda_trace.h"
+#include "camera.h"
+#include "trace.h"
+
+Renderer::Renderer(std::unique_ptr<Scene> scene) : m_scene(std::move(scene)) { }
+
+void Renderer::SetSampleCount(uint cnt)
+{
+    // the reference asserts that nothing is rendering (renderer.cpp:20); wait instead
+    WaitRendering();
+    m_sample_count = std::max(1u, cnt);
+}
+
+void Renderer::OnCancel()
+{
+    cuda_trace_cancel(m_scene->GetGrid()->GetDeviceContext());
+}
+
+void Renderer::RenderTile(Tile& tile)
+{
+    Tile *one = &tile;
+    RenderTiles(&one, 1);
+}
+
+void Renderer::RenderTiles(Tile * const *tiles, uint count)
+{
+    cuda_trace_ctx *ctx = m_scene->GetGrid()->GetDeviceContext();
+
+    // Per-frame inputs of the kernel (reference renderer.cpp:63-72,91-99)
+    cuda_trace_frame frame;
+    std::memset(&frame, 0, sizeof(frame));
+    float fov;
+    Matrix44f cam_mat;
+    m_scene->GetCameraParameters(fov, cam_mat);
+    frame.width = m_width;
+    frame.height = m_height;
+    frame.spp = m_sample_count;
+    frame.variant = m_variant;
+    frame.flags = m_gamma ? CUDA_TRACE_FLAG_GAMMA : 0u;
+    CameraFrameConstants(fov, m_width, m_height, frame.fov_xs, frame.aspect);
+    std::memcpy(frame.cam_mat, cam_mat.m_mat, sizeof(frame.cam_mat));
+
+    std::vector<cuda_trace_tile_rect> rects(count);
+    for (uint i = 0; i < count; i++)
+        tiles[i]->GetPosition(rects[i].x0, rects[i].y0, rects[i].x1, rects[i].y1);
+
+    m_frame.resize(size_t(m_width) * m_height);
+    const int rc = cuda_trace_tiles(ctx, &frame, rects.data(), count, m_frame.data());
+    if (rc == CUDA_TRACE_ERR_CANCELLED)
+        return;
+    if (rc)
+        throw std::runtime_error(std::string("Renderer: cuda_trace_tiles failed: ") + cuda_trace_last_error(ctx));
+    cuda_trace_last_kernel_ms(ctx, &m_last_kernel_ms);
+
+    // scatter into the tiles' own buffers (index x + y * tile_width, reference renderer.cpp:133)
+    for (uint i = 0; i < count; i++)
+    {
+        Tile& t = *tiles[i];
+        uint32 *dst = t.GetBuffer();
+        const uint tw = t.GetWidth();
+        for (uint y = 0; y < t.GetHeight(); y++)
+            std::memcpy(dst + size_t(y) * tw, &m_frame[rects[i].x0 + size_t(rects[i].y0 + y) * m_width], size_t(tw) * 4);
+    }
+}

@@ -164,6 +164,10 @@ int cuda_trace_sample_table(cuda_trace_ctx *ctx, uint32_t spp, float *xy);
 int cuda_trace_set_counting(cuda_trace_ctx *ctx, int enable);
 int cuda_trace_get_counters(cuda_trace_ctx *ctx, cuda_trace_counters *out);
 
+/* Measurement helper: evict the scene from L2 by overwriting a scratch buffer larger than L2
+ * (256 MiB cudaMemsetAsync on every device's stream).  Not part of the traced work. */
+int cuda_trace_flush_l2(cuda_trace_ctx *ctx);
+
 /* How many kernels this library has launched since cuda_trace_init (all devices) */
 uint64_t cuda_trace_kernel_launches(const cuda_trace_ctx *ctx);
 

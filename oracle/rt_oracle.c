@@ -45,6 +45,7 @@ static void cnt_add(rto_counters *dst, const rto_counters *src)
     dst->rej_det += src->rej_det;     dst->rej_u += src->rej_u;
     dst->rej_v += src->rej_v;         dst->full += src->full;
     dst->box_miss += src->box_miss;
+    dst->rep2 += src->rep2; dst->rep8 += src->rep8; dst->rep64 += src->rep64; dst->nonempty += src->nonempty;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -565,6 +566,8 @@ int rto_grid_intersect(const rto_scene *sc, const float *origin, const float *di
 
     /* :219-278 */
     *t = FLT_MAX;
+    uint32_t mbox[64];
+    uint32_t mbox_n = 0;
     for (;;)
     {
         const int sa = (next_t[0] < next_t[1]) ? ((next_t[0] < next_t[2]) ? 0 : 2)
@@ -572,9 +575,22 @@ int rto_grid_intersect(const rto_scene *sc, const float *origin, const float *di
         const uint64_t cell = (uint64_t) pos[0] + (uint64_t) pos[2] * g->dim[0] +
                               (uint64_t) pos[1] * g->dim[0] * g->dim[2];
         if (cnt) cnt->cells++;
+        if (cnt && g->cell_offset[cell] != g->cell_offset[cell + 1]) cnt->nonempty++;
         for (uint64_t k = g->cell_offset[cell]; k < g->cell_offset[cell + 1]; k++)
         {
             const uint32_t ci = g->tri_index[k];
+            if (cnt)
+            {
+                /* mailbox study only: how often was this triangle already tested by this ray? */
+                int found = -1;
+                for (uint32_t m = 0; m < mbox_n && m < 64; m++)
+                    if (mbox[(mbox_n - 1 - m) & 63] == ci) { found = (int) m; break; }
+                if (found >= 0 && found < 2) cnt->rep2++;
+                if (found >= 0 && found < 8) cnt->rep8++;
+                if (found >= 0) cnt->rep64++;
+                mbox[mbox_n & 63] = ci;
+                mbox_n++;
+            }
             const uint32_t *tr = sc->tri + (size_t) ci * 6;
             const float *v0 = sc->vtx + (size_t) tr[0] * 6;
             const float *v1 = sc->vtx + (size_t) tr[1] * 6;

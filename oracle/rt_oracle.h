@@ -55,6 +55,10 @@ typedef struct rto_counters
     uint64_t rej_v;      /* ... at the v stage                              */
     uint64_t full;       /* tests that computed t                           */
     uint64_t box_miss;   /* rays that missed the grid's box                 */
+    uint64_t rep2;       /* tests whose triangle was among the previous 2 tests' cells' ids (mailbox study) */
+    uint64_t rep8;       /* ... among the last 8 distinct ids tested by this ray */
+    uint64_t rep64;      /* ... among the last 64 */
+    uint64_t nonempty;   /* visited cells with a non-empty list */
 } rto_counters;
 
 enum { RTO_VARIANT_MT = 0 /* IntersectRayTri */, RTO_VARIANT_BARY = 1 /* IntersectRayTriBarycentric */ };
