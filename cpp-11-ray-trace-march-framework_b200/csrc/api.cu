@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -147,6 +148,8 @@ int finish_scene_on_device(cuda_trace_ctx *ctx, DeviceState& d)
     const uint64_t pcells = (uint64_t) (ctx->desc.dim[0] + 2) * (ctx->desc.dim[1] + 2) * (ctx->desc.dim[2] + 2);
     if (pcells >= (1ull << 31))
         return fail(ctx, CUDA_TRACE_ERR_ARG, "grid too large: padded cell count must stay below 2^31");
+    if (refs * 3 >= (1ull << 32))
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "grid too large: 3 x cell references must stay below 2^32");
     CK(cudaMalloc(&d.d_cell_occ, ((cells + 31) / 32) * sizeof(uint32_t)));
     CK(cudaMalloc(&d.d_pcell_start, (pcells + 1) * sizeof(uint32_t)));
     CK(cudaMalloc(&d.d_pcell_occ, ((pcells + 31) / 32) * sizeof(uint32_t)));
@@ -654,13 +657,55 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const
         p.spp = f->spp;
         p.gamma = (f->flags & CUDA_TRACE_FLAG_GAMMA) ? 1u : 0u;
         p.smp = d.d_smp;
+        // Where the padded occupancy map is read from (warp_trace.cuh): one byte per cell in shared
+        // memory when that leaves room for two 512-thread CTAs (or one 1024-thread CTA) per SM,
+        // else bits in shared memory, else bits through L1.  Tiny frames skip the per-CTA staging.
+        // CTA size: one 1024-thread CTA per SM measured best on every config (32 warps share one
+        // staged occupancy map and pull neighbouring strips, which keeps the triangle records of
+        // that screen region in L1); small frames use smaller CTAs so that every SM gets work.
+        int threads = 1024;
         {
-            // stage the padded occupancy bitmap in shared memory when it is small (res-64 grids: <= 36 KB)
             const uint64_t pcells = (uint64_t) (ctx->desc.dim[0] + 2) * (ctx->desc.dim[1] + 2) * (ctx->desc.dim[2] + 2);
-            const uint64_t words = (pcells + 31) / 32;
-            // (tiny frames: the per-CTA copy would cost more than it saves)
-            const bool big_frame = (uint64_t) f->width * f->height * f->spp >= (4u << 20);
-            p.occ_smem_words = (ctx->occ_in_smem && big_frame && words * 4 <= 40 * 1024) ? (uint32_t) words : 0u;
+            const uint64_t bit_words = (pcells + 31) / 32, byte_words = (pcells + 3) / 4;
+            const uint64_t rays = (uint64_t) f->width * f->height * f->spp;
+            const size_t smp_bytes = sizeof(float2) * f->spp;
+            const uint64_t strips_here = (total + (uint64_t) ctx->shard_world * n_dev - 1) / ((uint64_t) ctx->shard_world * n_dev);
+            while (threads > 64 && strips_here < (uint64_t) d.sm_count * (threads / 32))
+                threads /= 2;
+            p.occ_mode = kOccGlobalBits;
+            p.occ_smem_words = 0;
+            if (ctx->occ_in_smem && rays >= (4u << 20) && threads == 1024)
+            {
+                if (byte_words * 4 + smp_bytes <= 160 * 1024)
+                {
+                    p.occ_mode = kOccSmemBytes;
+                    p.occ_smem_words = (uint32_t) byte_words;
+                }
+                else if (bit_words * 4 + smp_bytes <= 160 * 1024)
+                {
+                    p.occ_mode = kOccSmemBits;
+                    p.occ_smem_words = (uint32_t) bit_words;
+                }
+            }
+            // tuning overrides (experiments only): RTM_OCC_MODE = 0 | 1 | 2, RTM_THREADS = CTA size
+            if (const char *e = std::getenv("RTM_OCC_MODE"))
+            {
+                const int m = std::atoi(e);
+                if (m == kOccGlobalBits) { p.occ_mode = kOccGlobalBits; p.occ_smem_words = 0; }
+                if (m == kOccSmemBits && bit_words * 4 + smp_bytes <= 200 * 1024) { p.occ_mode = kOccSmemBits; p.occ_smem_words = (uint32_t) bit_words; }
+                if (m == kOccSmemBytes && byte_words * 4 + smp_bytes <= 200 * 1024) { p.occ_mode = kOccSmemBytes; p.occ_smem_words = (uint32_t) byte_words; }
+            }
+            if (const char *e = std::getenv("RTM_THREADS"))
+            {
+                const int t = std::atoi(e);
+                if (t >= 32 && t <= 1024 && t % 32 == 0)
+                    threads = t;
+            }
+            // |det| <= |e1| |e2| |d| <= 3 extent^2: below 1e14 the reciprocal's fast path is always valid
+            float extent = 0.0f;
+            for (int k = 0; k < 3; k++)
+                extent = std::max(extent, ctx->desc.aabb_max[k] - ctx->desc.aabb_min[k]);
+            p.rcp_guard = (extent < 1.0e14f) ? 0u : 1u;
         }
         p.tile_rects = d.d_tile_rects;
         p.tile_strip_prefix = d.d_tile_prefix;
@@ -678,16 +723,15 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const
         p.hit_v = keep_hits ? ctx->d_hit_v : nullptr;
         p.counters = d.d_counters;
 
-        const int per_sm = std::max(1, trace_tiles_max_blocks_per_sm(f->variant, keep_hits, ctx->counting,
-                                                                       sizeof(float2) * f->spp + sizeof(uint32_t) * p.occ_smem_words,
-                                                                       p.occ_smem_words != 0));
+        const int per_sm = std::max(1, trace_tiles_max_blocks_per_sm(f->variant, keep_hits, ctx->counting, (int) p.occ_mode, threads,
+                                                                       trace_tiles_smem_bytes(f->spp, p.occ_smem_words)));
         const uint64_t my_strips = (total + p.shard_world - 1) / p.shard_world;
-        const uint64_t want = (my_strips + (kTraceThreads / 32) - 1) / (kTraceThreads / 32);
+        const uint64_t want = (my_strips + (threads / 32) - 1) / (threads / 32);
         const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) d.sm_count * per_sm, want));
         CK(cudaEventRecord(d.ev_begin, d.stream));
         if (total)
         {
-            launch_trace_tiles(p, f->variant, keep_hits, ctx->counting, blocks, d.stream);
+            launch_trace_tiles(p, f->variant, keep_hits, ctx->counting, blocks, threads, d.stream);
             ctx->launches++;
         }
         CK(cudaEventRecord(d.ev_end, d.stream));

@@ -21,8 +21,8 @@ namespace
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // One sample per lane; ALL lanes of the warp call this together (valid == false: no ray)
-template <int VARIANT, bool KEEP_HITS, bool COUNT, bool OCC_SMEM>
-__device__ __forceinline__ float3 trace_sample(const TraceParams& p, const uint32_t *s_occ, bool valid,
+template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE>
+__device__ __forceinline__ float3 trace_sample(const TraceParams& p, const void *s_occ, bool valid,
                                                uint32_t px, uint32_t py, uint32_t s, const float2 *smp, Counters *cnt)
 {
     float3 o, d;
@@ -32,7 +32,7 @@ __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const uint3
     hit.t = hit.u = hit.v = 0.0f;
     hit.tri = 0xFFFFFFFFu;
     if (COUNT && valid) cnt->rays++;
-    const bool is_hit = warp_grid_intersect<VARIANT, COUNT, OCC_SMEM>(p.grid, s_occ, o, d, valid, hit, cnt);
+    const bool is_hit = warp_grid_intersect<VARIANT, COUNT, OCC_MODE>(p.grid, s_occ, p.rcp_guard != 0, o, d, valid, hit, cnt);
     if (COUNT && is_hit) cnt->hits++;
     if (KEEP_HITS && valid)
     {
@@ -48,17 +48,25 @@ __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const uint3
     return rgb;
 }
 
-template <int VARIANT, bool KEEP_HITS, bool COUNT, bool OCC_SMEM>
-__global__ void __launch_bounds__(kTraceThreads) trace_tiles_kernel(const __grid_constant__ TraceParams p)
+template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE>
+__global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __grid_constant__ TraceParams p)
 {
     // shared memory: [sample table (renderer.cpp:49-60), spp x float2]
-    //                [padded occupancy bits (p.occ_smem_words; only when OCC_SMEM)]
+    //                [padded occupancy map: p.occ_smem_words 32-bit words of bits (mode 1) or of
+    //                 bytes, four cells per word (mode 2)]
     extern __shared__ float2 s_mem[];
     float2 *s_smp = s_mem;
     uint32_t *s_occ = reinterpret_cast<uint32_t *>(s_mem + p.spp);
-    if (OCC_SMEM)
+    if (OCC_MODE == kOccSmemBits)
         for (uint32_t i = threadIdx.x; i < p.occ_smem_words; i += blockDim.x)
             s_occ[i] = __ldg(&p.grid.pcell_occ[i]);
+    if (OCC_MODE == kOccSmemBytes)
+        for (uint32_t i = threadIdx.x; i < p.occ_smem_words; i += blockDim.x)
+        {
+            // expand 4 occupancy bits into 4 bytes (cells 4i .. 4i+3)
+            const uint32_t nib = (__ldg(&p.grid.pcell_occ[i >> 3]) >> ((i & 7u) * 4u)) & 0xFu;
+            s_occ[i] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        }
     for (uint32_t i = threadIdx.x; i < p.spp; i += blockDim.x)
         s_smp[i] = p.smp[i];
     __syncthreads();
@@ -113,7 +121,7 @@ __global__ void __launch_bounds__(kTraceThreads) trace_tiles_kernel(const __grid
                 if (!__any_sync(kFull, active))
                     continue;
                 const uint32_t px = bx0 + ox, py = by0 + oy;
-                const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_SMEM>(p, s_occ, active, px, py, s, s_smp, &cnt);
+                const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_MODE>(p, s_occ, active, px, py, s, s_smp, &cnt);
                 // col += sample, smp = 0..N-1 in order (renderer.cpp:87-122)
                 float3 acc = make_float3(0.0f, 0.0f, 0.0f);
                 const uint32_t base = pl * p.spp;
@@ -138,7 +146,7 @@ __global__ void __launch_bounds__(kTraceThreads) trace_tiles_kernel(const __grid
                 for (uint32_t sb = 0; sb < p.spp; sb += 32)
                 {
                     const uint32_t s = sb + lane;
-                    const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_SMEM>(p, s_occ, s < p.spp, px, py, s, s_smp, &cnt);
+                    const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_MODE>(p, s_occ, s < p.spp, px, py, s, s_smp, &cnt);
                     const uint32_t n = min(32u, p.spp - sb);
                     for (uint32_t k = 0; k < n; k++)
                     {
@@ -200,47 +208,46 @@ __global__ void sample_table_kernel(float2 *smp, uint32_t spp)
     smp[s] = make_float2((float) (x - 0.5), (float) (val - 0.5));
 }
 
-template <int VARIANT, bool KEEP_HITS, bool COUNT>
-void launch_one(const TraceParams& p, int grid_blocks, cudaStream_t stream)
+template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE>
+void launch_mode(const TraceParams& p, int grid_blocks, int threads, size_t smem, cudaStream_t stream)
 {
-    const size_t smem = sizeof(float2) * p.spp + sizeof(uint32_t) * p.occ_smem_words;
-    if (p.occ_smem_words)
-    {
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, true><<<grid_blocks, kTraceThreads, smem, stream>>>(p);
-    }
-    else
-    {
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, false><<<grid_blocks, kTraceThreads, smem, stream>>>(p);
-    }
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE><<<grid_blocks, threads, smem, stream>>>(p);
 }
 
 template <int VARIANT, bool KEEP_HITS, bool COUNT>
-int occupancy_one(size_t smem, bool occ_smem)
+void launch_one(const TraceParams& p, int grid_blocks, int threads, cudaStream_t stream)
+{
+    const size_t smem = trace_tiles_smem_bytes(p.spp, p.occ_smem_words);
+    if (p.occ_mode == kOccSmemBytes)
+        launch_mode<VARIANT, KEEP_HITS, COUNT, kOccSmemBytes>(p, grid_blocks, threads, smem, stream);
+    else if (p.occ_mode == kOccSmemBits)
+        launch_mode<VARIANT, KEEP_HITS, COUNT, kOccSmemBits>(p, grid_blocks, threads, smem, stream);
+    else
+        launch_mode<VARIANT, KEEP_HITS, COUNT, kOccGlobalBits>(p, grid_blocks, threads, smem, stream);
+}
+
+template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE>
+int occupancy_mode(int threads, size_t smem)
 {
     int n = 0;
-    if (occ_smem)
-    {
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, true>,
-                                                      kTraceThreads, smem);
-    }
-    else
-    {
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, false>,
-                                                      kTraceThreads, smem);
-    }
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE>, threads, smem);
     return n;
+}
+
+template <int VARIANT, bool KEEP_HITS, bool COUNT>
+int occupancy_one(int occ_mode, int threads, size_t smem)
+{
+    if (occ_mode == kOccSmemBytes)
+        return occupancy_mode<VARIANT, KEEP_HITS, COUNT, kOccSmemBytes>(threads, smem);
+    if (occ_mode == kOccSmemBits)
+        return occupancy_mode<VARIANT, KEEP_HITS, COUNT, kOccSmemBits>(threads, smem);
+    return occupancy_mode<VARIANT, KEEP_HITS, COUNT, kOccGlobalBits>(threads, smem);
 }
 
 } // namespace
@@ -261,15 +268,21 @@ int occupancy_one(size_t smem, bool occ_smem)
         }                                                                                        \
     } while (0)
 
-void launch_trace_tiles(const TraceParams& p, uint32_t variant, bool keep_hits, bool count, int grid_blocks,
-                        cudaStream_t stream)
+size_t trace_tiles_smem_bytes(uint32_t spp, uint32_t occ_smem_words)
 {
-    RTM_DISPATCH(launch_one, p, grid_blocks, stream);
+    return sizeof(float2) * spp + sizeof(uint32_t) * occ_smem_words;
 }
 
-int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count, size_t smem_bytes, bool occ_smem)
+void launch_trace_tiles(const TraceParams& p, uint32_t variant, bool keep_hits, bool count, int grid_blocks,
+                        int threads, cudaStream_t stream)
 {
-    RTM_DISPATCH(occupancy_one, smem_bytes, occ_smem);
+    RTM_DISPATCH(launch_one, p, grid_blocks, threads, stream);
+}
+
+int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count, int occ_mode, int threads,
+                                  size_t smem_bytes)
+{
+    RTM_DISPATCH(occupancy_one, occ_mode, threads, smem_bytes);
 }
 
 void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, cudaStream_t stream)

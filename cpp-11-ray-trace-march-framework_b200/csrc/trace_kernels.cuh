@@ -8,7 +8,14 @@ namespace rtm
 
 constexpr int kStripW = 8;        // a strip is an 8 x 4 pixel block of a tile
 constexpr int kStripH = 4;
-constexpr int kTraceThreads = 256; // 8 warps per CTA, one strip per warp at a time
+constexpr int kTraceMaxThreads = 1024; // launch bound (caps the kernel at 64 registers); actual CTA size is chosen per launch
+
+// Where the padded occupancy map lives (chosen per scene / frame by the launcher):
+//   0  bits in global memory, read through L1            (any grid size)
+//   1  bits staged in shared memory                      (<= ~1.6 M padded cells)
+//   2  one BYTE per cell in shared memory                (<= ~220 K padded cells, i.e. the res-64
+//      grids of configs C2-C4): the test is a single LDS.U8 without shift / mask arithmetic
+enum { kOccGlobalBits = 0, kOccSmemBits = 1, kOccSmemBytes = 2 };
 
 struct TraceParams
 {
@@ -17,7 +24,9 @@ struct TraceParams
     uint32_t width, height, spp;
     uint32_t gamma;
     const float2 *smp;                 // sample table, spp entries (K2)
-    uint32_t occ_smem_words;           // padded occupancy words staged in shared memory (0: read through L1)
+    uint32_t occ_mode;                 // kOccGlobalBits / kOccSmemBits / kOccSmemBytes (warp_trace.cuh)
+    uint32_t occ_smem_words;           // 32-bit words of the occupancy map staged in shared memory
+    uint32_t rcp_guard;                // 1: the scene extent allows |det| > 1e30, keep rcp_exact's range check
     const uint4 *tile_rects;           // n_tiles x {x0,y0,x1,y1}
     const uint32_t *tile_strip_prefix; // n_tiles + 1: first strip id of each tile
     uint32_t n_tiles;
@@ -41,8 +50,10 @@ struct RayBatchParams
 };
 
 void launch_trace_tiles(const TraceParams& p, uint32_t variant, bool keep_hits, bool count, int grid_blocks,
-                        cudaStream_t stream);
-int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count, size_t smem_bytes, bool occ_smem);
+                        int threads, cudaStream_t stream);
+int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count, int occ_mode, int threads,
+                                  size_t smem_bytes);
+size_t trace_tiles_smem_bytes(uint32_t spp, uint32_t occ_smem_words);
 void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, cudaStream_t stream);
 void launch_sample_table(float2 *smp, uint32_t spp, cudaStream_t stream);
 
