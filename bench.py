@@ -214,23 +214,13 @@ def run_ours(args, wl, rank, world, local_rank, dist):
     rects = capi.full_frame_tiles(w, h)
 
     # rank 0 owns the framebuffer; the others map it (CUDA IPC) and store into it over NVLink
-    if world > 1:
-        import torch
-        if rank == 0:
-            ct.prepare_framebuffer(w, h)
-            handle = [ct.export_framebuffer()]
-        else:
-            handle = [None]
-        dist.broadcast_object_list(handle, src=0)
-        if rank != 0:
-            ct.import_framebuffer(handle[0], w, h)
-        dist.barrier()
+    multirank = pkg("multirank")
+    group = multirank.RankGroup(dist, "cuda" if dist is not None else None)
+    multirank.share_framebuffer(ct, group, w, h)
+    barrier = group.barrier
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    host_fb = np.zeros((h, w), np.uint32)
+    pinned = capi.PinnedImage(w, h)  # page-locked host framebuffer: the D2H copy is one DMA
+    host_fb = pinned.array
 
     # warm-up (also first-touch of sample table, framebuffer, host registration)
     for _ in range(max(args.warmup, 3)):
@@ -255,14 +245,8 @@ def run_ours(args, wl, rank, world, local_rank, dist):
         step_ms[i] = ct.last_kernel_ms()
     barrier()
     launches = ct.kernel_launches() - launches0
-    if world > 1:
-        import torch
-        t = torch.tensor(step_ms, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms = t.cpu().numpy()
-        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
+    step_ms = group.allreduce_max(step_ms)      # a frame is done when its slowest rank is
+    launches = int(group.allreduce_sum([launches])[0])
     total_ms = float(step_ms.sum())
 
     # ---- end-to-end region: the reference-facing call with a host framebuffer
@@ -281,11 +265,7 @@ def run_ours(args, wl, rank, world, local_rank, dist):
             if rank == 0:
                 ct.read_framebuffer(host_fb)
         e2e_s += time.perf_counter() - t0
-    if world > 1:
-        import torch
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = float(group.allreduce_max([e2e_s])[0])
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- work counters of this frame (untimed, instrumented kernel) for the roofline figures

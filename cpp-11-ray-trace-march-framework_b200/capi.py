@@ -65,6 +65,8 @@ SYMBOLS = {
     "cuda_trace_sample_table": (C.c_int, [C.c_void_p, C.c_uint32, _F32P]),
     "cuda_trace_set_counting": (C.c_int, [C.c_void_p, C.c_int]),
     "cuda_trace_get_counters": (C.c_int, [C.c_void_p, C.POINTER(CountersC)]),
+    "cuda_trace_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "cuda_trace_host_free": (None, [C.c_void_p]),
     "cuda_trace_flush_l2": (C.c_int, [C.c_void_p]),
     "cuda_trace_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "cuda_trace_prepare_framebuffer": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
@@ -115,6 +117,27 @@ def full_frame_tiles(width, height, tiles_x=12, tiles_y=9):
             out.append((x * tw, y * th, width if x == tiles_x - 1 else (x + 1) * tw,
                         height if y == tiles_y - 1 else (y + 1) * th))
     return out
+
+
+class PinnedImage:
+    """[H, W] uint32 numpy view of page-locked host memory (cuda_trace_host_alloc)."""
+
+    def __init__(self, width, height):
+        self.lib = load_library()
+        self.ptr = self.lib.cuda_trace_host_alloc(width * height * 4)
+        if not self.ptr:
+            raise MemoryError("cuda_trace_host_alloc failed")
+        buf = (C.c_uint32 * (width * height)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, np.uint32).reshape(height, width)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self.lib.cuda_trace_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        self.close()
 
 
 class CudaTrace:

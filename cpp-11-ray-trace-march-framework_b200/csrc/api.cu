@@ -64,6 +64,7 @@ struct cuda_trace_ctx
     uint32_t num_vtx = 0, num_tri = 0;
 
     uint32_t shard_rank = 0, shard_world = 1;
+    uint32_t shard_chunk = 32; // consecutive strips dealt to one shard at a time (one CTA's worth of warps)
     bool counting = false;
     bool occ_in_smem = true;
     std::atomic<uint64_t> launches{0};
@@ -85,9 +86,6 @@ struct cuda_trace_ctx
     float last_kernel_ms = 0.0f;
     uint32_t *pinned_cancel_src = nullptr;
 
-    // cached registration of the caller's host framebuffer
-    void *registered_host = nullptr;
-    size_t registered_bytes = 0;
 };
 
 namespace
@@ -309,8 +307,6 @@ void cuda_trace_destroy(cuda_trace_ctx *ctx)
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
     }
-    if (ctx->registered_host)
-        cudaHostUnregister(ctx->registered_host);
     if (!ctx->dev.empty())
     {
         cudaSetDevice(ctx->dev[0].ordinal);
@@ -347,6 +343,8 @@ int cuda_trace_set_shard(cuda_trace_ctx *ctx, uint32_t rank, uint32_t world)
         return fail(ctx, CUDA_TRACE_ERR_ARG, "set_shard: need rank < world");
     ctx->shard_rank = rank;
     ctx->shard_world = world;
+    if (const char *e = std::getenv("RTM_SHARD_CHUNK")) // tuning override (experiments only)
+        ctx->shard_chunk = (uint32_t) std::max(1, std::atoi(e));
     return 0;
 }
 
@@ -548,7 +546,18 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const
     if (rc && rc != CUDA_TRACE_ERR_CANCELLED)
         return rc;
 
-    // strips per tile (8 x 4 pixel blocks, clipped to the tile)
+    // strips per tile (strip_w x strip_h pixel blocks, clipped to the tile)
+    uint32_t strip_w, strip_h;
+    strip_size_for_spp(f->spp, (uint64_t) f->width * f->height * f->spp, strip_w, strip_h);
+    if (const char *e = std::getenv("RTM_STRIP_PIXELS")) // tuning override (experiments only): 2,4,8,16,32
+    {
+        const uint32_t px = (uint32_t) std::atoi(e);
+        if (px == 2 || px == 4 || px == 8 || px == 16 || px == 32)
+        {
+            strip_w = px >= 32 ? 8 : (px >= 8 ? 4 : 2);
+            strip_h = px >= 16 ? 4 : (px >= 4 ? 2 : 1);
+        }
+    }
     std::vector<uint4> rects(n_tiles);
     std::vector<uint32_t> prefix(n_tiles + 1, 0);
     uint64_t total = 0;
@@ -559,7 +568,7 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const
             return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: tile " + std::to_string(i) + " outside the frame");
         rects[i] = make_uint4(t.x0, t.y0, t.x1, t.y1);
         prefix[i] = (uint32_t) total;
-        total += (uint64_t) ((t.x1 - t.x0 + kStripW - 1) / kStripW) * ((t.y1 - t.y0 + kStripH - 1) / kStripH);
+        total += (uint64_t) ((t.x1 - t.x0 + strip_w - 1) / strip_w) * ((t.y1 - t.y0 + strip_h - 1) / strip_h);
         if (total >= (1ull << 32))
             return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: too many strips");
     }
@@ -710,10 +719,13 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const
         p.tile_rects = d.d_tile_rects;
         p.tile_strip_prefix = d.d_tile_prefix;
         p.n_tiles = n_tiles;
+        p.strip_w = strip_w;
+        p.strip_h = strip_h;
         p.total_strips = (uint32_t) total;
         // strips are interleaved first over the processes (shard), then over this context's devices
         p.shard_world = ctx->shard_world * n_dev;
         p.shard_rank = ctx->shard_rank * n_dev + i;
+        p.shard_chunk = ctx->shard_chunk;
         p.strip_counter = d.d_strip_counter;
         p.cancel = d.d_cancel;
         p.framebuffer = ctx->d_fb;
@@ -796,21 +808,6 @@ int cuda_trace_read_framebuffer(cuda_trace_ctx *ctx, uint32_t *host_bgra)
     CK(cudaSetDevice(d0.ordinal));
     const uint32_t w = ctx->fb_w, h = ctx->fb_h;
     const size_t bytes = (size_t) w * h * sizeof(uint32_t);
-
-    // Pin the caller's buffer once (cached) so the copy is a straight DMA
-    if (ctx->registered_host != host_bgra || ctx->registered_bytes != bytes)
-    {
-        if (ctx->registered_host)
-            cudaHostUnregister(ctx->registered_host);
-        ctx->registered_host = nullptr;
-        if (cudaHostRegister(host_bgra, bytes, cudaHostRegisterDefault) == cudaSuccess)
-        {
-            ctx->registered_host = host_bgra;
-            ctx->registered_bytes = bytes;
-        }
-        else
-            cudaGetLastError(); // already pinned by the caller, or not registrable: plain copy
-    }
 
     // whole frame covered by a single tile list? then one copy, else one 2-D copy per tile
     uint64_t covered = 0;
@@ -921,6 +918,23 @@ int cuda_trace_sample_table(cuda_trace_ctx *ctx, uint32_t spp, float *xy)
     CK(cudaStreamSynchronize(d.stream));
     CK(cudaFree(d_smp));
     return 0;
+}
+
+void *cuda_trace_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void cuda_trace_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
 }
 
 int cuda_trace_flush_l2(cuda_trace_ctx *ctx)

@@ -82,7 +82,14 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         if (lane == 0)
             fetch = (*(volatile const uint32_t *) p.cancel) ? 0xFFFFFFFFu : atomicAdd(p.strip_counter, 1u);
         fetch = __shfl_sync(kFull, fetch, 0);
-        const uint64_t strip64 = (uint64_t) fetch * p.shard_world + p.shard_rank;
+        // the n-th strip of this shard: strips are dealt out in chunks of p.shard_chunk consecutive
+        // ids (neighbouring strips stay on one GPU / in one CTA: their rays share triangle records
+        // in L1), round-robin over the shards, the owner rotating from round to round so that
+        // regular cost patterns do not all land on the same shard
+        const uint32_t my_chunk = fetch / p.shard_chunk, in_chunk = fetch - my_chunk * p.shard_chunk;
+        const uint64_t chunk_id = (uint64_t) my_chunk * p.shard_world +
+                                  (p.shard_rank + p.shard_world - my_chunk % p.shard_world) % p.shard_world;
+        const uint64_t strip64 = chunk_id * p.shard_chunk + in_chunk;
         if (fetch == 0xFFFFFFFFu || strip64 >= p.total_strips)
             break;
         const uint32_t strip = (uint32_t) strip64;
@@ -96,13 +103,12 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         }
         const uint4 rect = __ldg(&p.tile_rects[lo]);
         const uint32_t local = strip - __ldg(&p.tile_strip_prefix[lo]);
-        const uint32_t strips_x = (rect.z - rect.x + kStripW - 1) / kStripW;
-        const uint32_t bx0 = rect.x + (local % strips_x) * kStripW;
-        const uint32_t by0 = rect.y + (local / strips_x) * kStripH;
-        const uint32_t bw = min((uint32_t) kStripW, rect.z - bx0);
-        const uint32_t bh = min((uint32_t) kStripH, rect.w - by0);
-        const uint32_t npix = bw * bh;
-        (void) npix;
+        const uint32_t strips_x = (rect.z - rect.x + p.strip_w - 1) / p.strip_w;
+        const uint32_t bx0 = rect.x + (local % strips_x) * p.strip_w;
+        const uint32_t by0 = rect.y + (local / strips_x) * p.strip_h;
+        const uint32_t bw = min(p.strip_w, rect.z - bx0);
+        const uint32_t bh = min(p.strip_h, rect.w - by0);
+        const uint32_t npix = bw * bh, slots = p.strip_w * p.strip_h;
 
         if (p.spp <= 32)
         {
@@ -112,12 +118,12 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
             // walk nearly the same cells.
             const uint32_t ppr = 32u / p.spp;
             const uint32_t pl = lane / p.spp, s = lane - pl * p.spp;
-            for (uint32_t pbase = 0; pbase < 32u; pbase += ppr)
+            for (uint32_t pbase = 0; pbase < slots; pbase += ppr)
             {
                 const uint32_t slot = pbase + pl;
                 const uint32_t ox = (slot & 1u) | ((slot >> 1) & 2u) | ((slot >> 2) & 4u);
                 const uint32_t oy = ((slot >> 1) & 1u) | ((slot >> 2) & 2u);
-                const bool active = pl < ppr && slot < 32u && ox < bw && oy < bh;
+                const bool active = pl < ppr && slot < slots && ox < bw && oy < bh;
                 if (!__any_sync(kFull, active))
                     continue;
                 const uint32_t px = bx0 + ox, py = by0 + oy;

@@ -9,6 +9,7 @@
 #include <string>
 
 #include "../../include/cuda_trace.h"
+#include "bmp_writer.h"
 #include "camera.h"
 #include "mesh.h"
 #include "renderer.h"
@@ -117,6 +118,11 @@ void rtm_mesh_add_instances(void *m, void *base, uint32 n, const float *params)
         inst.Transform(sc * ry * rx * tr);
         mesh->AddMesh(inst);
     }
+}
+
+int rtm_write_bitmap(const char *filename, uint32 width, uint32 height, const uint32 *bgra)
+{
+    return WriteBitmap(filename, width, height, bgra) ? 1 : 0;
 }
 
 // ---- renderer (Mesh -> Scene -> Renderer; takes ownership of the mesh handle)

@@ -11,6 +11,13 @@
 
 Renderer::Renderer(std::unique_ptr<Scene> scene) : m_scene(std::move(scene)) { }
 
+Renderer::~Renderer()
+{
+    KillAllWorkerThreads();
+    WaitRendering();
+    cuda_trace_host_free(m_frame);
+}
+
 void Renderer::SetSampleCount(uint cnt)
 {
     // the reference asserts that nothing is rendering (renderer.cpp:20); wait instead
@@ -51,8 +58,18 @@ void Renderer::RenderTiles(Tile * const *tiles, uint count)
     for (uint i = 0; i < count; i++)
         tiles[i]->GetPosition(rects[i].x0, rects[i].y0, rects[i].x1, rects[i].y1);
 
-    m_frame.resize(size_t(m_width) * m_height);
-    const int rc = cuda_trace_tiles(ctx, &frame, rects.data(), count, m_frame.data());
+    if (m_frame_pixels != size_t(m_width) * m_height)
+    {
+        cuda_trace_host_free(m_frame);
+        m_frame_pixels = size_t(m_width) * m_height;
+        m_frame = static_cast<uint32 *>(cuda_trace_host_alloc(m_frame_pixels * sizeof(uint32)));
+        if (!m_frame)
+        {
+            m_frame_pixels = 0;
+            throw std::runtime_error("Renderer: cannot allocate the host frame staging buffer");
+        }
+    }
+    const int rc = cuda_trace_tiles(ctx, &frame, rects.data(), count, m_frame);
     if (rc == CUDA_TRACE_ERR_CANCELLED)
         return;
     if (rc)

@@ -16,7 +16,7 @@ class Renderer : public Framebuffer
 {
 public:
     Renderer(std::unique_ptr<Scene> scene);
-    ~Renderer() { KillAllWorkerThreads(); WaitRendering(); }
+    ~Renderer();
 
     void SetSampleCount(uint cnt);
     uint GetSampleCount() const { return m_sample_count; }
@@ -39,7 +39,8 @@ protected:
     uint m_variant = 0;
     bool m_gamma = true;
     float m_last_kernel_ms = 0.0f;
-    std::vector<uint32> m_frame; // full-frame staging the device framebuffer is copied into
+    uint32 *m_frame = nullptr;   // page-locked full-frame staging the device framebuffer is copied into
+    size_t m_frame_pixels = 0;
 };
 
 #endif

@@ -16,6 +16,7 @@
 #ifndef CUDA_TRACE_H
 #define CUDA_TRACE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -97,8 +98,9 @@ void cuda_trace_destroy(cuda_trace_ctx *ctx);
 const char *cuda_trace_last_error(const cuda_trace_ctx *ctx); /* ctx may be NULL: last init error */
 int  cuda_trace_device_count(void);
 
-/* One-process-per-GPU operation (torchrun): this context renders only the strips
- * strip_id % world == rank of every frame.  Default rank 0 / world 1. */
+/* One-process-per-GPU operation (torchrun): this context renders only its share of every frame's
+ * strips -- chunks of 32 consecutive strips dealt round-robin over the world, the owner rotating
+ * from round to round.  Default rank 0 / world 1. */
 int cuda_trace_set_shard(cuda_trace_ctx *ctx, uint32_t rank, uint32_t world);
 
 /* ---- scene ----------------------------------------------------------------------------------
@@ -163,6 +165,12 @@ int cuda_trace_sample_table(cuda_trace_ctx *ctx, uint32_t spp, float *xy);
  * (slower kernel variant).  cuda_trace_get_counters returns those of the last frame. */
 int cuda_trace_set_counting(cuda_trace_ctx *ctx, int enable);
 int cuda_trace_get_counters(cuda_trace_ctx *ctx, cuda_trace_counters *out);
+
+/* Page-locked host memory for the framebuffer passed to cuda_trace_tiles / read_framebuffer: the
+ * device-to-host copy is then a single DMA at full PCIe rate.  Any other host memory works too
+ * (the driver stages it), only slower.  Free with cuda_trace_host_free. */
+void *cuda_trace_host_alloc(size_t bytes);
+void  cuda_trace_host_free(void *p);
 
 /* Measurement helper: evict the scene from L2 by overwriting a scratch buffer larger than L2
  * (256 MiB cudaMemsetAsync on every device's stream).  Not part of the traced work. */

@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
-inputs.  Bar: per-sample hit record (tri_idx, t, u, v) bit-exact; 8-bit image bit-exact except
-where IEEE sqrtf differs from glibc powf(x, .5f) (documented: <= 1 LSB)."""
+inputs.  Bar: per-sample hit record (tri_idx, t, u, v) bit-exact AND the 8-bit image bit-exact
+(north_star tolerance: hit index exact up to 0.01 % ties, image within 1 LSB on 99.9 % of pixels --
+both are met with zero exceptions on every case here)."""
 import numpy as np
 import pytest
 
@@ -68,8 +69,9 @@ def test_scene_parity_small(cuda_trace, port, scene_data, name, variant):
     assert np.array_equal(t.view(np.uint32), o["t"].view(np.uint32))
     assert np.array_equal(u.view(np.uint32), o["u"].view(np.uint32))
     assert np.array_equal(v.view(np.uint32), o["v"].view(np.uint32))
-    ndiff, maxd = image_diff(img, o["bgra"])
-    assert maxd <= 1 and ndiff <= 0.001 * w * h, (ndiff, maxd)
+    # 8-bit output: IEEE sqrtf vs glibc powf(x, .5f) never changes a byte for x in [0, 1.12]
+    # (exhaustive scan, tests/test_oracle_vs_ref.py), so the image is bit-exact too
+    assert image_diff(img, o["bgra"]) == (0, 0)
 
 
 @pytest.mark.parametrize("spp", [1, 2, 3, 5, 16, 32, 33, 70])
@@ -82,8 +84,7 @@ def test_sample_counts(cuda_trace, port, scene_data, spp):
     tri, t, u, v = cuda_trace.download_hits(w, h, spp)
     o = port.scene(sd.vtx, sd.tri, 64).render(sd.cam16, sd.fov, w, h, spp, want_hits=True)
     assert np.array_equal(tri, o["tri"])
-    ndiff, maxd = image_diff(img, o["bgra"])
-    assert maxd <= 1 and ndiff <= max(1, 0.001 * w * h), (ndiff, maxd)
+    assert image_diff(img, o["bgra"]) == (0, 0)
 
 
 def test_ragged_tiles_and_untouched_pixels(cuda_trace, port, scene_data):
@@ -99,8 +100,7 @@ def test_ragged_tiles_and_untouched_pixels(cuda_trace, port, scene_data):
     for x0, y0, x1, y1 in rects:
         mask[y0:y1, x0:x1] = True
     assert (out[~mask] == 0xDEADBEEF).all()
-    ndiff, maxd = image_diff(out[mask], o[mask])
-    assert maxd <= 1 and ndiff <= 2
+    assert np.array_equal(out[mask], o[mask])
     # empty tile list is legal and renders nothing
     out2 = np.full((h, w), 7, np.uint32)
     cuda_trace.trace_tiles(f, [], out=out2)
