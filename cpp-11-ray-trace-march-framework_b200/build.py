@@ -78,8 +78,26 @@ def build_host(force=False, verbose=False):
     return LIB_HOST
 
 
+CLI = os.path.join(PKG, "rtm_render")
+
+
+def build_cli(force=False, verbose=False):
+    """rtm_render: headless command-line renderer on the host API (tools/rtm_render.cpp)."""
+    src = os.path.join(ROOT, "tools", "rtm_render.cpp")
+    if not force and not _newer(CLI, [src, LIB_HOST]):
+        return CLI
+    cmd = [CXX] + CXX_FLAGS + ["-o", CLI, src, "-I" + HOST, "-L" + PKG, "-lrtm_host", "-lcuda_trace",
+                               "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("g++ failed: " + " ".join(cmd))
+    return CLI
+
+
 def build_all(force=False, verbose=False):
-    return [build_cuda(force, verbose), build_host(force, verbose)]
+    return [build_cuda(force, verbose), build_host(force, verbose), build_cli(force, verbose)]
 
 
 if __name__ == "__main__":

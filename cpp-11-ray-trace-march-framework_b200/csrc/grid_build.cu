@@ -211,6 +211,16 @@ __device__ __forceinline__ void tri_range(const float *__restrict__ vtx, const u
         mn = std_min(mn, c[k]); mx = std_max(mx, c[k]);
         const uint32_t s = __float2uint_rz((mn - g.aabb_min[k]) / g.cell_wdh);
         uint32_t e = __float2uint_rz((mx - g.aabb_min[k]) / g.cell_wdh);
+        // The reference seeds the maximum with FLT_MIN (> 0), so for a triangle whose coordinates
+        // on this axis are all negative its candidate range runs on to the cell containing 0 --
+        // thousands of cells the exact test then rejects one by one.  Membership is decided by
+        // that test alone (it contains the per-axis interval test, aabb_tri_internal.h:154-166),
+        // so the range may be cut at the triangle's TRUE maximum plus one guard cell without
+        // changing a single list; the wider range only costs time (26 s -> well under a second
+        // for the 50 M-triangle soup at 256^3).
+        const float true_mx = std_max(std_max(a[k], b[k]), c[k]);
+        const uint32_t e_true = __float2uint_rz((true_mx - g.aabb_min[k]) / g.cell_wdh) + 1u;
+        if (e > e_true) e = e_true;
         // the reference does not clamp `end` (it relies on the 1e-4 growth, grid.cpp:18-30);
         // clamping cannot change the result because cells outside the grid do not exist
         if (e > g.dim[k] - 1) e = g.dim[k] - 1;

@@ -280,8 +280,12 @@ class Port:
         n = self.lib.rto_powf_vs_sqrtf(lo_bits, hi_bits, n_threads or (os.cpu_count() or 1), C.byref(bd))
         return int(n), int(bd.value)
 
-    def scene(self, vtx, tri, grid_res=64, grid=None, n_threads=0):
-        return PortScene(self, vtx, tri, grid_res, grid, n_threads)
+    def scene(self, vtx, tri, grid_res=64, grid=None, n_threads=0, tight_ranges=False):
+        C.c_int.in_dll(self.lib, "rto_grid_build_tight_ranges").value = int(tight_ranges)
+        try:
+            return PortScene(self, vtx, tri, grid_res, grid, n_threads)
+        finally:
+            C.c_int.in_dll(self.lib, "rto_grid_build_tight_ranges").value = 0
 
 
 class PortScene:

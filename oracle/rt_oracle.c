@@ -339,6 +339,8 @@ static int tri_aabb_overlap(const float *v0, const float *v1, const float *v2, c
     return rto_tri_box_overlap(center, half, tri);
 }
 
+int rto_grid_build_tight_ranges = 0;
+
 typedef struct pair_list
 {
     uint64_t *cell;
@@ -392,6 +394,17 @@ static void *build_worker(void *arg)
             tmax[k] = mx - g->aabb_min[k];
             start[k] = (uint32_t) (tmin[k] / g->cell_wdh);
             end[k] = (uint32_t) (tmax[k] / g->cell_wdh);
+            if (rto_grid_build_tight_ranges)
+            {
+                /* Optional (off by default, so the port stays the literal algorithm): cut the
+                 * candidate range at the triangle's true maximum + 1 guard cell.  The lists cannot
+                 * change -- the SAT alone decides membership -- but the reference's FLT_MIN-seeded
+                 * maximum makes the literal loop take minutes on large all-negative-octant scenes.
+                 * tests/test_oracle_vs_ref.py checks both modes give identical grids. */
+                const float true_mx = std_max(std_max(v0[k], v1[k]), v2[k]);
+                const uint32_t e_true = (uint32_t) ((true_mx - g->aabb_min[k]) / g->cell_wdh) + 1u;
+                if (end[k] > e_true) end[k] = e_true;
+            }
         }
         for (uint32_t x = start[0]; x <= end[0]; x++)
             for (uint32_t y = start[1]; y <= end[1]; y++)

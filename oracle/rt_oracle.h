@@ -85,6 +85,7 @@ int rto_ray_tri_bary(const float *o, const float *d, const float *v0, const floa
 /* a9: grid.cpp:12-154 (+ triangle.h:116-131, aabb.h:15-32, aabb_tri_internal.h:42-186,
  * mesh.cpp:72-94).  Fills scene->grid; returns 0 on success */
 int  rto_grid_build(rto_scene *scene, uint32_t grid_res, uint32_t n_threads);
+extern int rto_grid_build_tight_ranges; /* 1: cut candidate ranges at the true triangle maximum (same lists, faster) */
 void rto_grid_free(rto_grid *grid);
 int  rto_tri_box_overlap(const double center[3], const double half[3], const double tri[3][3]);
 

@@ -70,6 +70,17 @@ def test_grid_build_other_resolutions(port, ref, res):
         assert np.array_equal(np.asarray(g[k]), np.asarray(pg[k])), k
 
 
+def test_tight_candidate_ranges_give_identical_grids(port, scene_data):
+    """The literal port enumerates the reference's (FLT_MIN-seeded, hence huge) candidate ranges;
+    its optional tight mode and the GPU build cut them at the true triangle maximum.  Same lists."""
+    for name, res in (("killeroo", 64), ("tiger_soup_small", 48), ("cornell", 64), ("head", 33)):
+        sd = scene_data(name)
+        a = port.scene(sd.vtx, sd.tri, res).grid()
+        b = port.scene(sd.vtx, sd.tri, res, tight_ranges=True).grid()
+        for k in a:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (name, k)
+
+
 @pytest.mark.parametrize("name", PRESETS)
 def test_render_matches_reference(port, ref, name):
     """Image through the reference's own Renderer/worker pool, and per-sample hit records through
