@@ -21,7 +21,7 @@ namespace
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // One sample per lane; ALL lanes of the warp call this together (valid == false: no ray)
-template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE>
+template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE, bool RCP_GUARD>
 __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const void *s_occ, bool valid,
                                                uint32_t px, uint32_t py, uint32_t s, const float2 *smp, Counters *cnt)
 {
@@ -32,7 +32,7 @@ __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const void 
     hit.t = hit.u = hit.v = 0.0f;
     hit.tri = 0xFFFFFFFFu;
     if (COUNT && valid) cnt->rays++;
-    const bool is_hit = warp_grid_intersect<VARIANT, COUNT, OCC_MODE>(p.grid, s_occ, p.rcp_guard != 0, o, d, valid, hit, cnt);
+    const bool is_hit = warp_grid_intersect<VARIANT, COUNT, OCC_MODE, RCP_GUARD>(p.grid, s_occ, o, d, valid, hit, cnt);
     if (COUNT && is_hit) cnt->hits++;
     if (KEEP_HITS && valid)
     {
@@ -48,7 +48,7 @@ __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const void 
     return rgb;
 }
 
-template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE>
+template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE, bool RCP_GUARD>
 __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __grid_constant__ TraceParams p)
 {
     // shared memory: [sample table (renderer.cpp:49-60), spp x float2]
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
                 if (!__any_sync(kFull, active))
                     continue;
                 const uint32_t px = bx0 + ox, py = by0 + oy;
-                const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_MODE>(p, s_occ, active, px, py, s, s_smp, &cnt);
+                const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_MODE, RCP_GUARD>(p, s_occ, active, px, py, s, s_smp, &cnt);
                 // col += sample, smp = 0..N-1 in order (renderer.cpp:87-122)
                 float3 acc = make_float3(0.0f, 0.0f, 0.0f);
                 const uint32_t base = pl * p.spp;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
                 for (uint32_t sb = 0; sb < p.spp; sb += 32)
                 {
                     const uint32_t s = sb + lane;
-                    const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_MODE>(p, s_occ, s < p.spp, px, py, s, s_smp, &cnt);
+                    const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_MODE, RCP_GUARD>(p, s_occ, s < p.spp, px, py, s, s_smp, &cnt);
                     const uint32_t n = min(32u, p.spp - sb);
                     for (uint32_t k = 0; k < n; k++)
                     {
@@ -214,13 +214,24 @@ __global__ void sample_table_kernel(float2 *smp, uint32_t spp)
     smp[s] = make_float2((float) (x - 0.5), (float) (val - 0.5));
 }
 
+// The rcp range guard (scenes larger than 1e14 units) is only instantiated for the plain kernel;
+// the instrumented variants always keep it.
 template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE>
 void launch_mode(const TraceParams& p, int grid_blocks, int threads, size_t smem, cudaStream_t stream)
 {
+    constexpr bool kPlain = !KEEP_HITS && !COUNT;
+    if (kPlain && !p.rcp_guard)
+    {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, !kPlain>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, !kPlain><<<grid_blocks, threads, smem, stream>>>(p);
+        return;
+    }
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE>,
+        cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE><<<grid_blocks, threads, smem, stream>>>(p);
+    trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true><<<grid_blocks, threads, smem, stream>>>(p);
 }
 
 template <int VARIANT, bool KEEP_HITS, bool COUNT>
@@ -240,9 +251,9 @@ int occupancy_mode(int threads, size_t smem)
 {
     int n = 0;
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE>,
+        cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE>, threads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true>, threads, smem);
     return n;
 }
 
