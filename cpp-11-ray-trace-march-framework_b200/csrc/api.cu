@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -48,6 +49,12 @@ struct DeviceState
     uint32_t *d_cancel = nullptr;
     Counters *d_counters = nullptr;
     void *d_l2_scratch = nullptr;
+    // cost-ordered scheduling (schedule.cu): cycles per strip of the last frame -> order of the next
+    uint32_t *d_strip_cycles = nullptr, *d_fetch_order = nullptr, *d_order_scratch = nullptr;
+    unsigned long long *d_cost_sum = nullptr;
+    uint32_t order_cap = 0;
+    bool order_valid = false;
+    std::vector<uint32_t> order_signature;
     bool frame_pending = false;
 };
 
@@ -67,6 +74,7 @@ struct cuda_trace_ctx
     uint32_t shard_chunk = 32; // consecutive strips dealt to one shard at a time (one CTA's worth of warps)
     bool counting = false;
     bool occ_in_smem = true;
+    int cost_order_forced = -1; // schedule.cu: -1 automatic, 0 / 1 forced by RTM_COST_ORDER (experiments)
     std::atomic<uint64_t> launches{0};
 
     // framebuffer (device 0, or an imported IPC mapping of another process' framebuffer)
@@ -284,6 +292,8 @@ int cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **
     if ((e = cudaHostAlloc(&ctx->pinned_cancel_src, sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
         return bail(std::string("cudaHostAlloc: ") + cudaGetErrorString(e), CUDA_TRACE_ERR_CUDA);
     *ctx->pinned_cancel_src = 1;
+    if (const char *e = std::getenv("RTM_COST_ORDER"))
+        ctx->cost_order_forced = std::atoi(e) != 0 ? 1 : 0;
     *out = ctx;
     return 0;
 }
@@ -321,6 +331,7 @@ void cuda_trace_destroy(cuda_trace_ctx *ctx)
         free_scene(d);
         cudaFree(d.d_smp); cudaFree(d.d_tile_rects); cudaFree(d.d_tile_prefix); cudaFree(d.d_strip_counter);
         cudaFree(d.d_cancel); cudaFree(d.d_counters); cudaFree(d.d_l2_scratch);
+        cudaFree(d.d_strip_cycles); cudaFree(d.d_fetch_order); cudaFree(d.d_cost_sum); cudaFree(d.d_order_scratch);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
         if (d.stream) cudaStreamDestroy(d.stream);
@@ -735,6 +746,52 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const
         p.hit_v = keep_hits ? ctx->d_hit_v : nullptr;
         p.counters = d.d_counters;
 
+        {
+            const uint64_t chunks_total = (total + p.shard_chunk - 1) / p.shard_chunk;
+            const uint64_t my_chunks = (chunks_total + p.shard_world - 1) / p.shard_world;
+            if (my_chunks * p.shard_chunk >= (1ull << 32))
+                return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: too many strips");
+            p.shard_strips = (uint32_t) (my_chunks * p.shard_chunk);
+
+            // cost order from the previous frame, valid only if that frame had the same layout
+            const uint32_t shard_strips = p.shard_strips;
+            std::vector<uint32_t> sig = { f->width, f->height, f->spp, n_tiles, (uint32_t) total, strip_w, strip_h,
+                                          p.shard_rank, p.shard_world, p.shard_chunk, shard_strips };
+            for (uint32_t k = 0; k < n_tiles; k++)
+            {
+                sig.push_back(rects[k].x ^ (rects[k].z << 16));
+                sig.push_back(rects[k].y ^ (rects[k].w << 16));
+            }
+            p.fetch_order = nullptr;
+            p.strip_cycles = nullptr;
+            // worth its ~1 % instrumentation cost when the frame is sharded or small (the tail of
+            // expensive strips is then a large part of the launch); RTM_COST_ORDER=0/1 forces it
+            const bool want_order = ctx->cost_order_forced >= 0 ? ctx->cost_order_forced != 0
+                                   : (p.shard_world > 1 || (uint64_t) f->width * f->height * f->spp < (64ull << 20));
+            if (want_order && shard_strips > 0)
+            {
+                if (d.order_cap < shard_strips)
+                {
+                    cudaFree(d.d_strip_cycles); cudaFree(d.d_fetch_order); cudaFree(d.d_order_scratch);
+                    d.d_strip_cycles = d.d_fetch_order = d.d_order_scratch = nullptr;
+                    d.order_cap = 0;
+                    d.order_valid = false;
+                    CK(cudaMalloc(&d.d_strip_cycles, sizeof(uint32_t) * shard_strips));
+                    CK(cudaMalloc(&d.d_fetch_order, sizeof(uint32_t) * shard_strips));
+                    CK(cudaMalloc(&d.d_order_scratch, sizeof(uint32_t) * strip_order_scratch_words(shard_strips)));
+                    if (!d.d_cost_sum)
+                        CK(cudaMalloc(&d.d_cost_sum, sizeof(unsigned long long)));
+                    d.order_cap = shard_strips;
+                }
+                if (d.order_valid && sig == d.order_signature)
+                    p.fetch_order = d.d_fetch_order;
+                d.order_signature = sig;
+                p.strip_cycles = d.d_strip_cycles;
+                CK(cudaMemsetAsync(d.d_strip_cycles, 0, sizeof(uint32_t) * shard_strips, d.stream));
+            }
+            else
+                d.order_valid = false;
+        }
         const int per_sm = std::max(1, trace_tiles_max_blocks_per_sm(f->variant, keep_hits, ctx->counting, (int) p.occ_mode, threads,
                                                                        trace_tiles_smem_bytes(f->spp, p.occ_smem_words)));
         const uint64_t my_strips = (total + p.shard_world - 1) / p.shard_world;
@@ -747,6 +804,14 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const
             ctx->launches++;
         }
         CK(cudaEventRecord(d.ev_end, d.stream));
+        if (p.strip_cycles && total)
+        {
+            // this frame's strip costs -> next frame's visiting order (off the timed kernel)
+            launch_build_strip_order(d.d_strip_cycles, (uint32_t) d.order_signature[10], d.d_cost_sum, d.d_order_scratch,
+                                     d.d_fetch_order, d.stream);
+            ctx->launches += 4;
+            d.order_valid = true;
+        }
         CK(cudaGetLastError());
         d.frame_pending = true;
     }

@@ -75,13 +75,21 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
     const float spp_f = (float) p.spp;
     Counters cnt = { 0, 0, 0, 0 };
 
+    const uint32_t slots = p.strip_w * p.strip_h;
     for (;;)
     {
         // dynamic strip scheduler: one atomic per strip per warp
-        uint32_t fetch = 0;
+        uint32_t visit = 0;
         if (lane == 0)
-            fetch = (*(volatile const uint32_t *) p.cancel) ? 0xFFFFFFFFu : atomicAdd(p.strip_counter, 1u);
-        fetch = __shfl_sync(kFull, fetch, 0);
+            visit = (*(volatile const uint32_t *) p.cancel) ? 0xFFFFFFFFu : atomicAdd(p.strip_counter, 1u);
+        visit = __shfl_sync(kFull, visit, 0);
+        if (visit == 0xFFFFFFFFu || visit >= p.shard_strips)
+            break;
+        // `fetch` = index of the strip within this shard, taken through the cost order of the
+        // previous frame when there is one (schedule.cu)
+        const uint32_t fetch = p.fetch_order ? __ldg(&p.fetch_order[visit]) : visit;
+        const long long t_begin = p.strip_cycles ? clock64() : 0;
+        const uint32_t slot_begin = 0, slot_end = slots;
         // the n-th strip of this shard: strips are dealt out in chunks of p.shard_chunk consecutive
         // ids (neighbouring strips stay on one GPU / in one CTA: their rays share triangle records
         // in L1), round-robin over the shards, the owner rotating from round to round so that
@@ -90,8 +98,8 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         const uint64_t chunk_id = (uint64_t) my_chunk * p.shard_world +
                                   (p.shard_rank + p.shard_world - my_chunk % p.shard_world) % p.shard_world;
         const uint64_t strip64 = chunk_id * p.shard_chunk + in_chunk;
-        if (fetch == 0xFFFFFFFFu || strip64 >= p.total_strips)
-            break;
+        if (strip64 >= p.total_strips)
+            continue;
         const uint32_t strip = (uint32_t) strip64;
 
         // which tile? (upper bound over the per-tile strip prefix)
@@ -108,7 +116,6 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         const uint32_t by0 = rect.y + (local / strips_x) * p.strip_h;
         const uint32_t bw = min(p.strip_w, rect.z - bx0);
         const uint32_t bh = min(p.strip_h, rect.w - by0);
-        const uint32_t npix = bw * bh, slots = p.strip_w * p.strip_h;
 
         if (p.spp <= 32)
         {
@@ -118,12 +125,12 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
             // walk nearly the same cells.
             const uint32_t ppr = 32u / p.spp;
             const uint32_t pl = lane / p.spp, s = lane - pl * p.spp;
-            for (uint32_t pbase = 0; pbase < slots; pbase += ppr)
+            for (uint32_t pbase = slot_begin; pbase < slot_end; pbase += ppr)
             {
                 const uint32_t slot = pbase + pl;
                 const uint32_t ox = (slot & 1u) | ((slot >> 1) & 2u) | ((slot >> 2) & 4u);
                 const uint32_t oy = ((slot >> 1) & 1u) | ((slot >> 2) & 2u);
-                const bool active = pl < ppr && slot < slots && ox < bw && oy < bh;
+                const bool active = pl < ppr && slot < slot_end && ox < bw && oy < bh;
                 if (!__any_sync(kFull, active))
                     continue;
                 const uint32_t px = bx0 + ox, py = by0 + oy;
@@ -145,9 +152,13 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         else
         {
             // one pixel at a time, 32 samples per round
-            for (uint32_t pix = 0; pix < npix; pix++)
+            for (uint32_t slot = slot_begin; slot < slot_end; slot++)
             {
-                const uint32_t px = bx0 + pix % bw, py = by0 + pix / bw;
+                const uint32_t ox = (slot & 1u) | ((slot >> 1) & 2u) | ((slot >> 2) & 4u);
+                const uint32_t oy = ((slot >> 1) & 1u) | ((slot >> 2) & 2u);
+                if (ox >= bw || oy >= bh)
+                    continue;
+                const uint32_t px = bx0 + ox, py = by0 + oy;
                 float3 acc = make_float3(0.0f, 0.0f, 0.0f);
                 for (uint32_t sb = 0; sb < p.spp; sb += 32)
                 {
@@ -165,6 +176,8 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
                     p.framebuffer[(size_t) py * p.width + px] = resolve_pixel(acc, spp_f, p.gamma != 0);
             }
         }
+        if (p.strip_cycles && lane == 0)
+            p.strip_cycles[fetch] = (uint32_t) min(clock64() - t_begin, 0x7FFFFFFFll);
     }
 
     if (COUNT)

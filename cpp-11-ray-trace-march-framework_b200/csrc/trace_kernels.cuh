@@ -43,9 +43,12 @@ struct TraceParams
     const uint32_t *tile_strip_prefix; // n_tiles + 1: first strip id of each tile
     uint32_t n_tiles;
     uint32_t strip_w, strip_h;         // see strip_size_for_spp
+    uint32_t shard_strips;             // strips this launch may fetch (upper bound; out-of-range ids are skipped)
     uint32_t total_strips;
     uint32_t shard_rank, shard_world;  // this launch renders the strips of shard `rank` out of `world`
     uint32_t shard_chunk;              // consecutive strips per deal (see trace_tiles_kernel)
+    const uint32_t *fetch_order;       // cost-ordered visiting order of this shard's strips (schedule.cu) or null
+    uint32_t *strip_cycles;            // out: cycles spent per strip of this shard (feeds the next frame's order) or null
     uint32_t *strip_counter;           // dynamic strip scheduler (zeroed before launch)
     const uint32_t *cancel;            // non-zero => stop fetching strips
     uint32_t *framebuffer;             // width * height, row 0 = y 0 (may be a peer / IPC pointer)
@@ -70,6 +73,11 @@ int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count, 
 size_t trace_tiles_smem_bytes(uint32_t spp, uint32_t occ_smem_words);
 void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, cudaStream_t stream);
 void launch_sample_table(float2 *smp, uint32_t spp, cudaStream_t stream);
+
+// cost-ordered scheduling (schedule.cu): 4 kernels; scratch = 2 * ceil(n / 1024) + 2 words
+void launch_build_strip_order(const uint32_t *cycles, uint32_t n, unsigned long long *sum, uint32_t *scratch,
+                              uint32_t *order, cudaStream_t stream);
+size_t strip_order_scratch_words(uint32_t n);
 
 // scene packing (pack.cu)
 void launch_pack_cell_tris(const float *vtx, const uint32_t *tri, const uint32_t *tri_index, uint64_t num_refs,

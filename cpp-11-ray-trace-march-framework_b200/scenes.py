@@ -144,7 +144,7 @@ CONFIGS = {
     "C2": ("killeroo", 1920, 1080, 4, 64),
     "C3": ("torusknot", 1920, 1080, 16, 64),
     "C4": ("room", 3840, 2160, 16, 64),
-    "C5": ("tiger_soup", 3840, 2160, 16, 256),
+    "C5": ("tiger_soup", 3840, 2160, 16, 512),
     "killeroo4k": ("killeroo", 3840, 2160, 16, 64),
 }
 

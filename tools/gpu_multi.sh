@@ -2,7 +2,7 @@
 # Multi-GPU session: tests + scaling bench at N = 1, 2 (and up to the GPUs present).  bash tools/gpu_multi.sh tag
 TAG=${1:-multi}; OUT=gpurun_out/$TAG; mkdir -p $OUT; cd $GRAFT_REPO_ROOT
 NG=$(nvidia-smi -L | wc -l); echo "GPUs: $NG"
-timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 | tee $OUT/pytest_gpu.txt
+timeout 1200 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -8 | tee $OUT/pytest_gpu.txt
 for WL in killeroo4k C4; do
 for N in 1 2 4 8; do
   [ $N -gt $NG ] && continue
