@@ -250,20 +250,27 @@ def run_ours(args, wl, rank, world, local_rank, dist):
     total_ms = float(step_ms.sum())
 
     # ---- end-to-end region: the reference-facing call with a host framebuffer
+    if world > 1:
+        # every rank now also counts its finished strips per row band behind rank 0's framebuffer
+        # (system-scope release, a few % of kernel time), so that rank 0 can ship bands to the host
+        # while the frame is still being traced and needs no barrier before the read-back
+        ct.set_shard_signals(True)
+        barrier()
     e2e_s = 0.0
     for i in range(args.steps):
         ct.flush_l2()
         ct.sync()
         barrier()
         t0 = time.perf_counter()
-        if world == 1:
+        if rank == 0:
+            # the reference-facing call: returns when the whole frame is in the HOST buffer.  Row bands
+            # are copied out as soon as every rank's strips of that band are finished (no barrier
+            # between tracing and read-back)
             ct.trace_tiles(frame, rects, out=host_fb)
         else:
             ct.trace_tiles_async(frame, rects)
             ct.sync()
-            barrier()
-            if rank == 0:
-                ct.read_framebuffer(host_fb)
+        barrier()
         e2e_s += time.perf_counter() - t0
     e2e_s = float(group.allreduce_max([e2e_s])[0])
     clocks = sampler.stop() if rank == 0 else None

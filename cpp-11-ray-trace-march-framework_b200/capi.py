@@ -49,6 +49,7 @@ SYMBOLS = {
     "cuda_trace_last_error": (C.c_char_p, [C.c_void_p]),
     "cuda_trace_device_count": (C.c_int, []),
     "cuda_trace_set_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "cuda_trace_set_shard_signals": (C.c_int, [C.c_void_p, C.c_int]),
     "cuda_trace_upload_scene": (C.c_int, [C.c_void_p, _F32P, C.c_uint32, _U32P, C.c_uint32, C.c_uint32]),
     "cuda_trace_upload_scene_with_grid": (C.c_int, [C.c_void_p, _F32P, C.c_uint32, _U32P, C.c_uint32,
                                                     C.POINTER(GridDesc), _U64P, _U32P]),
@@ -295,6 +296,9 @@ class CudaTrace:
 
     def set_shard(self, rank, world):
         self._ck(self.lib.cuda_trace_set_shard(self.h, rank, world))
+
+    def set_shard_signals(self, enable):
+        self._ck(self.lib.cuda_trace_set_shard_signals(self.h, int(enable)))
 
     def prepare_framebuffer(self, width, height):
         self._ck(self.lib.cuda_trace_prepare_framebuffer(self.h, width, height))

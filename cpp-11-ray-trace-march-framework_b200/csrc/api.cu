@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -30,6 +31,8 @@ struct DeviceState
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t side_stream = nullptr; // cancel flag writes while the main stream is busy
+    cudaStream_t copy_stream = nullptr; // overlapped framebuffer read-back (device 0 only)
+    cudaEvent_t ev_copy = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 
     // scene
@@ -81,6 +84,18 @@ struct cuda_trace_ctx
     uint32_t *d_fb = nullptr;
     bool fb_imported = false;
     uint32_t fb_w = 0, fb_h = 0;
+
+    // Overlapped read-back: the framebuffer allocation carries kMaxBands completion counters
+    // behind the pixels (so IPC peers reach them through the same mapping).  K1 bumps a band's
+    // counter once per finished strip; band_expected is the running total rank 0 waits for.
+    uint32_t band_rows = 1, n_bands = 1;
+    uint32_t band_expected[kMaxBands] = {};
+    std::vector<uint32_t> band_inc_sig;
+    uint32_t band_inc[kMaxBands] = {};
+    bool copy_pending = false;
+    bool overlap_d2h = true;      // RTM_OVERLAP_D2H=0 disables
+    bool shard_signals = false;   // cuda_trace_set_shard_signals: other ranks bump the counters too
+    int (*wait_value32)(cudaStream_t, unsigned long long, unsigned int, unsigned int) = nullptr;
 
     // per-sample hit records of the last KEEP_HITS frame (device 0)
     uint32_t *d_hit_tri = nullptr;
@@ -198,6 +213,9 @@ int check_mesh_args(cuda_trace_ctx *ctx, const float *vertices, uint32_t num_ver
     return 0;
 }
 
+size_t fb_pixel_bytes(uint32_t w, uint32_t h) { return ((size_t) w * h * sizeof(uint32_t) + 255) & ~(size_t) 255; }
+size_t fb_alloc_bytes(uint32_t w, uint32_t h) { return fb_pixel_bytes(w, h) + kMaxBands * sizeof(uint32_t); }
+
 int ensure_framebuffer(cuda_trace_ctx *ctx, uint32_t w, uint32_t h)
 {
     if (ctx->d_fb && ctx->fb_w == w && ctx->fb_h == h)
@@ -208,11 +226,36 @@ int ensure_framebuffer(cuda_trace_ctx *ctx, uint32_t w, uint32_t h)
     if (ctx->d_fb)
         CK(cudaFree(ctx->d_fb));
     ctx->d_fb = nullptr;
-    CK(cudaMalloc(&ctx->d_fb, (size_t) w * h * sizeof(uint32_t)));
-    CK(cudaMemsetAsync(ctx->d_fb, 0, (size_t) w * h * sizeof(uint32_t), ctx->dev[0].stream));
+    CK(cudaMalloc(&ctx->d_fb, fb_alloc_bytes(w, h)));
+    CK(cudaMemsetAsync(ctx->d_fb, 0, fb_alloc_bytes(w, h), ctx->dev[0].stream));
     ctx->fb_w = w;
     ctx->fb_h = h;
+    std::memset(ctx->band_expected, 0, sizeof(ctx->band_expected));
     return 0;
+}
+
+uint32_t *band_counters(cuda_trace_ctx *ctx)
+{
+    return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(ctx->d_fb) + fb_pixel_bytes(ctx->fb_w, ctx->fb_h));
+}
+
+// Strips per row band for this frame layout (a strip that straddles a band boundary counts in
+// both, exactly as the kernel bumps both)
+void band_increments(const std::vector<uint4>& rects, uint32_t strip_w, uint32_t strip_h, uint32_t band_rows,
+                     uint32_t *inc)
+{
+    std::memset(inc, 0, sizeof(uint32_t) * kMaxBands);
+    for (const uint4& r : rects)
+    {
+        const uint32_t nx = (r.z - r.x + strip_w - 1) / strip_w;
+        for (uint32_t y = r.y; y < r.w; y += strip_h)
+        {
+            const uint32_t b0 = y / band_rows, b1 = (std::min(y + strip_h, r.w) - 1) / band_rows;
+            inc[b0] += nx;
+            if (b1 != b0)
+                inc[b1] += nx;
+        }
+    }
 }
 
 } // namespace
@@ -267,6 +310,8 @@ int cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **
         d.sm_count = prop.multiProcessorCount;
         if ((e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&d.side_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.ev_copy, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreate(&d.ev_begin)) != cudaSuccess || (e = cudaEventCreate(&d.ev_end)) != cudaSuccess ||
             (e = cudaMalloc(&d.d_strip_counter, sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMalloc(&d.d_cancel, sizeof(uint32_t))) != cudaSuccess ||
@@ -292,6 +337,18 @@ int cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **
     if ((e = cudaHostAlloc(&ctx->pinned_cancel_src, sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
         return bail(std::string("cudaHostAlloc: ") + cudaGetErrorString(e), CUDA_TRACE_ERR_CUDA);
     *ctx->pinned_cancel_src = 1;
+    {
+        // stream-ordered "wait until *addr >= value" (driver API), used by the overlapped read-back
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            ctx->wait_value32 = reinterpret_cast<int (*)(cudaStream_t, unsigned long long, unsigned int, unsigned int)>(fn);
+        else
+            cudaGetLastError();
+        if (const char *e = std::getenv("RTM_OVERLAP_D2H"))
+            ctx->overlap_d2h = std::atoi(e) != 0;
+    }
     if (const char *e = std::getenv("RTM_COST_ORDER"))
         ctx->cost_order_forced = std::atoi(e) != 0 ? 1 : 0;
     *out = ctx;
@@ -316,6 +373,7 @@ void cuda_trace_destroy(cuda_trace_ctx *ctx)
     {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
+        if (d.copy_stream && !ctx->shard_signals) cudaStreamSynchronize(d.copy_stream);
     }
     if (!ctx->dev.empty())
     {
@@ -336,6 +394,8 @@ void cuda_trace_destroy(cuda_trace_ctx *ctx)
         if (d.ev_end) cudaEventDestroy(d.ev_end);
         if (d.stream) cudaStreamDestroy(d.stream);
         if (d.side_stream) cudaStreamDestroy(d.side_stream);
+        if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+        if (d.ev_copy) cudaEventDestroy(d.ev_copy);
     }
     if (ctx->pinned_cancel_src)
         cudaFreeHost(ctx->pinned_cancel_src);
@@ -356,6 +416,14 @@ int cuda_trace_set_shard(cuda_trace_ctx *ctx, uint32_t rank, uint32_t world)
     ctx->shard_world = world;
     if (const char *e = std::getenv("RTM_SHARD_CHUNK")) // tuning override (experiments only)
         ctx->shard_chunk = (uint32_t) std::max(1, std::atoi(e));
+    return 0;
+}
+
+int cuda_trace_set_shard_signals(cuda_trace_ctx *ctx, int enable)
+{
+    if (!ctx)
+        return CUDA_TRACE_ERR_ARG;
+    ctx->shard_signals = enable != 0;
     return 0;
 }
 
@@ -542,8 +610,8 @@ int cuda_trace_set_counting(cuda_trace_ctx *ctx, int enable)
     return 0;
 }
 
-int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const cuda_trace_tile_rect *tiles,
-                           uint32_t n_tiles)
+static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const cuda_trace_tile_rect *tiles,
+                            uint32_t n_tiles, uint32_t *host_bgra)
 {
     if (!ctx || !f || (!tiles && n_tiles))
         return CUDA_TRACE_ERR_ARG;
@@ -620,6 +688,34 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const
     ctx->frame = *f;
     ctx->tiles.assign(tiles, tiles + n_tiles);
     ctx->frame_valid = true;
+
+    // Overlapped read-back: row bands whose strips are all finished are copied to the host while
+    // the rest of the frame is still being traced.  Needs the whole frame covered by the tile list
+    // and, when the frame is sharded over processes, every rank signalling (set_shard_signals).
+    uint64_t covered = 0;
+    for (uint32_t i = 0; i < n_tiles; i++)
+        covered += (uint64_t) (tiles[i].x1 - tiles[i].x0) * (tiles[i].y1 - tiles[i].y0);
+    const bool can_overlap = host_bgra && ctx->overlap_d2h && ctx->wait_value32 && !ctx->fb_imported && total > 0 &&
+                             covered >= (uint64_t) f->width * f->height && (ctx->shard_world == 1 || ctx->shard_signals);
+    const bool use_bands = ctx->shard_signals || can_overlap || std::getenv("RTM_FORCE_BANDS") != nullptr;
+    if (use_bands)
+    {
+        ctx->band_rows = std::max<uint32_t>(strip_h, (f->height + 15) / 16);
+        ctx->n_bands = (f->height + ctx->band_rows - 1) / ctx->band_rows;
+        std::vector<uint32_t> bsig = { f->width, f->height, strip_w, strip_h, n_tiles, ctx->band_rows };
+        for (uint32_t k = 0; k < n_tiles; k++)
+        {
+            bsig.push_back(rects[k].x ^ (rects[k].z << 16));
+            bsig.push_back(rects[k].y ^ (rects[k].w << 16));
+        }
+        if (bsig != ctx->band_inc_sig)
+        {
+            band_increments(rects, strip_w, strip_h, ctx->band_rows, ctx->band_inc);
+            ctx->band_inc_sig = bsig;
+        }
+        for (uint32_t b = 0; b < ctx->n_bands; b++)
+            ctx->band_expected[b] += ctx->band_inc[b]; // counters are monotone across frames (wrap-safe compare)
+    }
 
     const uint32_t n_dev = (uint32_t) ctx->dev.size();
     for (uint32_t i = 0; i < n_dev; i++)
@@ -740,6 +836,9 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const
         p.strip_counter = d.d_strip_counter;
         p.cancel = d.d_cancel;
         p.framebuffer = ctx->d_fb;
+        p.band_done = use_bands ? band_counters(ctx) : nullptr;
+        p.band_rows = ctx->band_rows;
+        p.band_scope_sys = (ctx->fb_imported || i > 0 || ctx->shard_signals || std::getenv("RTM_BAND_SYS")) ? 1u : 0u;
         p.hit_tri = keep_hits ? ctx->d_hit_tri : nullptr;
         p.hit_t = keep_hits ? ctx->d_hit_t : nullptr;
         p.hit_u = keep_hits ? ctx->d_hit_u : nullptr;
@@ -815,7 +914,30 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const
         CK(cudaGetLastError());
         d.frame_pending = true;
     }
+
+    if (can_overlap)
+    {
+        DeviceState& d0 = ctx->dev[0];
+        CK(cudaSetDevice(d0.ordinal));
+        uint32_t *counters = band_counters(ctx);
+        for (uint32_t b = 0; b < ctx->n_bands; b++)
+        {
+            const uint32_t y0 = b * ctx->band_rows, y1 = std::min(f->height, y0 + ctx->band_rows);
+            if (ctx->wait_value32(d0.copy_stream, (unsigned long long) (uintptr_t) (counters + b), ctx->band_expected[b],
+                                  0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
+                return fail(ctx, CUDA_TRACE_ERR_CUDA, "cuStreamWaitValue32 failed");
+            CK(cudaMemcpyAsync(host_bgra + (size_t) y0 * f->width, ctx->d_fb + (size_t) y0 * f->width,
+                               (size_t) (y1 - y0) * f->width * sizeof(uint32_t), cudaMemcpyDeviceToHost, d0.copy_stream));
+        }
+        ctx->copy_pending = true;
+    }
     return 0;
+}
+
+int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const cuda_trace_tile_rect *tiles,
+                           uint32_t n_tiles)
+{
+    return tiles_async_impl(ctx, f, tiles, n_tiles, nullptr);
 }
 
 int cuda_trace_sync(cuda_trace_ctx *ctx)
@@ -839,6 +961,12 @@ int cuda_trace_sync(cuda_trace_ctx *ctx)
             d.frame_pending = false;
             any = true;
         }
+    }
+    if (ctx->copy_pending)
+    {
+        CK(cudaSetDevice(ctx->dev[0].ordinal));
+        CK(cudaStreamSynchronize(ctx->dev[0].copy_stream));
+        ctx->copy_pending = false;
     }
     if (any)
         ctx->last_kernel_ms = ms_max;
@@ -896,12 +1024,13 @@ int cuda_trace_read_framebuffer(cuda_trace_ctx *ctx, uint32_t *host_bgra)
 int cuda_trace_tiles(cuda_trace_ctx *ctx, const cuda_trace_frame *frame, const cuda_trace_tile_rect *tiles,
                      uint32_t n_tiles, uint32_t *host_bgra)
 {
-    int rc = cuda_trace_tiles_async(ctx, frame, tiles, n_tiles);
+    int rc = tiles_async_impl(ctx, frame, tiles, n_tiles, host_bgra);
     if (rc)
         return rc;
+    const bool overlapped = ctx->copy_pending; // the bands are already on their way to host_bgra
     if ((rc = cuda_trace_sync(ctx)))
         return rc;
-    if (host_bgra)
+    if (host_bgra && !overlapped)
         return cuda_trace_read_framebuffer(ctx, host_bgra);
     return 0;
 }

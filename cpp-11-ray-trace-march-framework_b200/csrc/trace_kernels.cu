@@ -48,6 +48,19 @@ __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const void 
     return rgb;
 }
 
+// All lanes call this; lane 0 adds `count` to the band's completion counter with release semantics
+__device__ __forceinline__ void publish_band(const TraceParams& p, uint32_t lane, uint32_t band, uint32_t count)
+{
+    __syncwarp();
+    if (lane == 0)
+    {
+        if (p.band_scope_sys)
+            asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(count) : "memory");
+        else
+            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(count) : "memory");
+    }
+}
+
 template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE, bool RCP_GUARD>
 __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __grid_constant__ TraceParams p)
 {
@@ -76,14 +89,21 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
     Counters cnt = { 0, 0, 0, 0 };
 
     const uint32_t slots = p.strip_w * p.strip_h;
+    uint32_t pend_band = 0, pend_count = 0; // finished strips not yet published (see publish_band)
     for (;;)
     {
         // dynamic strip scheduler: one atomic per strip per warp
-        uint32_t visit = 0;
+        // A cancelled frame still walks its strip list -- without tracing -- so that the per-band
+        // completion counts the read-back waits on are reached (framebuffer.h:32 m_threads_stop)
+        uint32_t visit = 0, cancelled = 0;
         if (lane == 0)
-            visit = (*(volatile const uint32_t *) p.cancel) ? 0xFFFFFFFFu : atomicAdd(p.strip_counter, 1u);
+        {
+            cancelled = *(volatile const uint32_t *) p.cancel;
+            visit = atomicAdd(p.strip_counter, 1u);
+        }
         visit = __shfl_sync(kFull, visit, 0);
-        if (visit == 0xFFFFFFFFu || visit >= p.shard_strips)
+        cancelled = __shfl_sync(kFull, cancelled, 0);
+        if (visit >= p.shard_strips || (cancelled && !p.band_done))
             break;
         // `fetch` = index of the strip within this shard, taken through the cost order of the
         // previous frame when there is one (schedule.cu)
@@ -117,7 +137,11 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         const uint32_t bw = min(p.strip_w, rect.z - bx0);
         const uint32_t bh = min(p.strip_h, rect.w - by0);
 
-        if (p.spp <= 32)
+        if (cancelled)
+        {
+            // nothing rendered, but the strip counts as finished for the read-back
+        }
+        else if (p.spp <= 32)
         {
             // 32 / spp whole pixels per round; lane = (pixel in round) * spp + sample.  The 32
             // pixel slots of the 8x4 strip are visited in 2x2-quad (Morton) order, so the pixels
@@ -178,7 +202,28 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         }
         if (p.strip_cycles && lane == 0)
             p.strip_cycles[fetch] = (uint32_t) min(clock64() - t_begin, 0x7FFFFFFFll);
+        if (p.band_done)
+        {
+            // Publish "these strips' pixels are stored" per row band.  Finished strips are batched
+            // per warp (same band, up to 8) because the publication is a release: a warp barrier
+            // orders every lane's pixel stores before lane 0's release-increment, whose fence is
+            // the expensive part (system scope when the counter lives on another GPU / process).
+            // The host's copy stream waits on these counters and ships each row band to the host
+            // while later bands are still being traced.
+            const uint32_t b0 = by0 / p.band_rows, b1 = (by0 + bh - 1) / p.band_rows;
+            if (pend_count && (pend_band != b0 || pend_count >= 8u))
+            {
+                publish_band(p, lane, pend_band, pend_count);
+                pend_count = 0;
+            }
+            pend_band = b0;
+            pend_count++;
+            if (b1 != b0)
+                publish_band(p, lane, b1, 1u); // a strip straddling two bands counts in both
+        }
     }
+    if (p.band_done && pend_count)
+        publish_band(p, lane, pend_band, pend_count);
 
     if (COUNT)
     {

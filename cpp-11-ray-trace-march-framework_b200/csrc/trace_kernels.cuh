@@ -20,6 +20,7 @@ inline void strip_size_for_spp(uint32_t spp, uint64_t frame_rays, uint32_t& w, u
     w = pixels >= 32 ? 8 : (pixels >= 8 ? 4 : 2);
     h = pixels >= 16 ? 4 : (pixels >= 4 ? 2 : 1);
 }
+constexpr int kMaxBands = 32;          // row bands of the overlapped framebuffer read-back (api.cu)
 constexpr int kTraceMaxThreads = 1024; // launch bound (caps the kernel at 64 registers); actual CTA size is chosen per launch
 
 // Where the padded occupancy map lives (chosen per scene / frame by the launcher):
@@ -52,6 +53,10 @@ struct TraceParams
     uint32_t *strip_counter;           // dynamic strip scheduler (zeroed before launch)
     const uint32_t *cancel;            // non-zero => stop fetching strips
     uint32_t *framebuffer;             // width * height, row 0 = y 0 (may be a peer / IPC pointer)
+    uint32_t *band_done;               // per row band: strips finished so far (monotone across frames; lives behind the
+                                       // framebuffer, so peers / other ranks reach it through the same mapping) or null
+    uint32_t band_rows;                // rows per band
+    uint32_t band_scope_sys;           // 1: counters / pixels may live on another GPU (system-scope release), 0: local
     uint32_t *hit_tri;                 // optional per-sample records (KEEP_HITS)
     float *hit_t, *hit_u, *hit_v;
     Counters *counters;                // optional (COUNT)

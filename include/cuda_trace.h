@@ -103,6 +103,13 @@ int  cuda_trace_device_count(void);
  * from round to round.  Default rank 0 / world 1. */
 int cuda_trace_set_shard(cuda_trace_ctx *ctx, uint32_t rank, uint32_t world);
 
+/* Sharded frames with an overlapped gather: when enabled on EVERY rank, each rank's kernel counts its
+ * finished strips per row band in counters that live behind rank 0's framebuffer (reached through
+ * the imported mapping), and rank 0's cuda_trace_tiles() copies each band to the host as soon as
+ * all ranks' strips of that band are in -- no barrier between tracing and read-back.  The ranks
+ * must still not start frame i+1 before rank 0's call for frame i has returned. */
+int cuda_trace_set_shard_signals(cuda_trace_ctx *ctx, int enable);
+
 /* ---- scene ----------------------------------------------------------------------------------
  * Replaces Scene::Scene -> Grid::Grid(mesh, grid_res) (scene.cpp:6-10, grid.cpp:12-154) and the
  * double indirection Grid::Intersect / RenderTile do per triangle (grid.cpp:245-253,

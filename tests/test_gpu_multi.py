@@ -90,6 +90,23 @@ if rank == 0:
     assert np.array_equal(img, ref_img), "sharded frame differs from the single-GPU frame"
     print("sharded frame ok", int((img != 0).sum()))
 group.barrier()
+# overlapped gather: every rank signals finished strips per row band; rank 0's trace_tiles() copies
+# each band to the host as soon as all ranks' strips of it are in (no barrier before the read-back)
+ct.set_shard_signals(True)
+pinned = capi.PinnedImage(w, h)
+for it in range(4):
+    pinned.array[:] = 0
+    group.barrier()
+    if rank == 0:
+        ct.trace_tiles(frame, out=pinned.array)
+        assert np.array_equal(pinned.array, ref_img), "overlapped gather differs (iteration %d)" % it
+    else:
+        ct.trace_tiles_async(frame)
+        ct.sync()
+    group.barrier()
+if rank == 0:
+    print("overlapped gather ok")
+pinned.close()
 ct.close()
 dist.destroy_process_group()
 '''
@@ -110,4 +127,4 @@ def test_one_process_per_gpu_ipc_gather(two_gpus, tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "sharded frame ok" in r.stdout
+    assert "sharded frame ok" in r.stdout and "overlapped gather ok" in r.stdout
