@@ -51,6 +51,7 @@ SYMBOLS = {
     "cuda_trace_set_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "cuda_trace_set_shard_signals": (C.c_int, [C.c_void_p, C.c_int]),
     "cuda_trace_upload_scene": (C.c_int, [C.c_void_p, _F32P, C.c_uint32, _U32P, C.c_uint32, C.c_uint32]),
+    "cuda_trace_suggest_grid_res": (C.c_uint32, [C.c_uint32]),
     "cuda_trace_upload_scene_with_grid": (C.c_int, [C.c_void_p, _F32P, C.c_uint32, _U32P, C.c_uint32,
                                                     C.POINTER(GridDesc), _U64P, _U32P]),
     "cuda_trace_download_grid": (C.c_int, [C.c_void_p, C.POINTER(GridDesc), _U64P, _U32P]),
@@ -64,6 +65,10 @@ SYMBOLS = {
     "cuda_trace_intersect_rays": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, C.c_uint32, _U32P, _F32P,
                                             _F32P, _F32P]),
     "cuda_trace_sample_table": (C.c_int, [C.c_void_p, C.c_uint32, _F32P]),
+    "cuda_trace_qmc_sequence": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _U32P, C.c_uint32, C.c_uint32, C.c_uint32,
+                                          C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]),
+    "cuda_trace_qmc_cranley_patterson": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_double, C.c_uint32,
+                                                   C.POINTER(C.c_double)]),
     "cuda_trace_set_counting": (C.c_int, [C.c_void_p, C.c_int]),
     "cuda_trace_get_counters": (C.c_int, [C.c_void_p, C.POINTER(CountersC)]),
     "cuda_trace_host_alloc": (C.c_void_p, [C.c_size_t]),
@@ -279,6 +284,33 @@ class CudaTrace:
         xy = np.zeros((spp, 2), np.float32)
         self._ck(self.lib.cuda_trace_sample_table(self.h, spp, _p(xy, _F32P)))
         return xy
+
+    # -- QMC sample tables (the reference's sampling module)
+    QMC_KINDS = {"halton": 0, "hammersley": 1, "halton_zaremba": 2, "hammersley_zaremba": 3, "base2": 4, "sobol": 5,
+                 "larcher_pillichshammer": 6}
+    QMC_SCRAMBLES = {"none": 0, "braaten_weller": 1, "faure": 2, "reverse": 3, "custom": 4}
+
+    def qmc_sequence(self, kind, n_begin, count, dim_begin=0, dim_count=1, num_smp=1, bits=0, scramble="none",
+                     perm=None, perm_primes=0):
+        """-> float64 [count, dim_count].  scramble "braaten_weller" loads assets/sampling/braaten_weller_16.u32
+        unless ``perm`` is given; "custom" needs ``perm`` (tables of the first ``perm_primes`` primes back to back)."""
+        k, s = self.QMC_KINDS[kind], self.QMC_SCRAMBLES[scramble]
+        if s == 1 and perm is None:
+            path = os.path.join(os.path.dirname(PKG), "assets", "sampling", "braaten_weller_16.u32")
+            perm, perm_primes = np.fromfile(path, np.uint32), 16
+        if perm is not None:
+            perm = np.ascontiguousarray(perm, np.uint32)
+        out = np.zeros((count, dim_count), np.float64)
+        self._ck(self.lib.cuda_trace_qmc_sequence(self.h, k, s, _p(perm, _U32P), perm_primes, n_begin, count, dim_begin,
+                                                  dim_count, num_smp, bits, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def qmc_cranley_patterson(self, x, e):
+        x = np.ascontiguousarray(x, np.float64)
+        out = np.zeros_like(x)
+        self._ck(self.lib.cuda_trace_qmc_cranley_patterson(self.h, x.ctypes.data_as(C.POINTER(C.c_double)), float(e),
+                                                           x.size, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
 
     def set_counting(self, enable):
         self._ck(self.lib.cuda_trace_set_counting(self.h, int(enable)))

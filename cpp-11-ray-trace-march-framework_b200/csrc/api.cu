@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <mutex>
@@ -16,6 +17,7 @@
 #include <vector>
 
 #include "grid_build.cuh"
+#include "qmc.cuh"
 #include "trace_kernels.cuh"
 
 using namespace rtm;
@@ -76,6 +78,7 @@ struct cuda_trace_ctx
     uint32_t shard_rank = 0, shard_world = 1;
     uint32_t shard_chunk = 32; // consecutive strips dealt to one shard at a time (one CTA's worth of warps)
     bool counting = false;
+    bool qmc_ready = false; // prime table uploaded to constant memory (qmc.cu)
     bool occ_in_smem = true;
     int cost_order_forced = -1; // schedule.cu: -1 automatic, 0 / 1 forced by RTM_COST_ORDER (experiments)
     std::atomic<uint64_t> launches{0};
@@ -467,6 +470,12 @@ int cuda_trace_upload_scene(cuda_trace_ctx *ctx, const float *vertices, uint32_t
     }
     ctx->have_scene = true;
     return 0;
+}
+
+uint32_t cuda_trace_suggest_grid_res(uint32_t num_triangles)
+{
+    const double r = std::cbrt(3.0 * (double) num_triangles);
+    return (uint32_t) std::min(640.0, std::max(16.0, std::floor(r + 0.5)));
 }
 
 int cuda_trace_upload_scene_with_grid(cuda_trace_ctx *ctx, const float *vertices, uint32_t num_vertices,
@@ -1143,6 +1152,99 @@ int cuda_trace_flush_l2(cuda_trace_ctx *ctx)
             CK(cudaMalloc(&d.d_l2_scratch, bytes));
         CK(cudaMemsetAsync(d.d_l2_scratch, 0xA5, bytes, d.stream));
     }
+    return 0;
+}
+
+int cuda_trace_qmc_sequence(cuda_trace_ctx *ctx, uint32_t kind, uint32_t scramble, const uint32_t *perm,
+                            uint32_t perm_primes, uint32_t n_begin, uint32_t count, uint32_t dim_begin,
+                            uint32_t dim_count, uint32_t num_smp, uint32_t bits, double *out)
+{
+    if (!ctx || (!out && count && dim_count) || kind > 6 || scramble > 4)
+        return CUDA_TRACE_ERR_ARG;
+    const bool table_kind = kind <= 3;
+    if (table_kind && ((uint64_t) dim_begin + dim_count > (uint64_t) kQmcPrimes))
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "qmc_sequence: dimension beyond the 1000-prime table");
+    if ((kind == 1 || kind == 3) && num_smp == 0)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "qmc_sequence: Hammersley needs num_smp > 0");
+    const bool caller_table = kind <= 1 && (scramble == kQmcScrambleBraatenWeller || scramble == kQmcScrambleCustom);
+    if (caller_table && (!perm || perm_primes == 0 || perm_primes > (uint32_t) kQmcPrimes))
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "qmc_sequence: this scramble needs the caller's permutation tables");
+    if ((uint64_t) count * dim_count == 0)
+        return 0;
+    DeviceState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.ordinal));
+    if (!ctx->qmc_ready)
+    {
+        CK(qmc_upload_primes());
+        ctx->qmc_ready = true;
+    }
+
+    // permutation tables: offsets = running sum of the primes
+    const std::vector<uint32_t> primes = qmc_primes();
+    std::vector<uint32_t> table, offset;
+    uint32_t n_primes = 0;
+    if (kind <= 1 && scramble != kQmcScrambleNone)
+    {
+        n_primes = caller_table ? perm_primes : 128u; // FAURE_TBL_SIZE = REVERSE_TBL_SIZE = 128 (sampling.h:52,67)
+        offset.resize(n_primes + 1, 0);
+        for (uint32_t i = 0; i < n_primes; i++)
+            offset[i + 1] = offset[i] + primes[i];
+        if (caller_table)
+        {
+            table.assign(perm, perm + offset[n_primes]);
+            for (uint32_t i = 0; i < n_primes; i++)
+                for (uint32_t k = offset[i]; k < offset[i + 1]; k++)
+                    if (table[k] >= primes[i]) // each table permutes the digits 0 .. prime-1
+                        return fail(ctx, CUDA_TRACE_ERR_ARG, "qmc_sequence: permutation entry out of range");
+        }
+        else if (scramble == kQmcScrambleFaure)
+            for (uint32_t i = 0; i < n_primes; i++)
+            {
+                const std::vector<uint32_t> f = qmc_faure_permutation(primes[i]);
+                table.insert(table.end(), f.begin(), f.end());
+            }
+        else
+            table.assign(1, 0u); // reverse is a formula, the table is not read
+    }
+    uint32_t *d_table = nullptr, *d_offset = nullptr;
+    double *d_out = nullptr;
+    const size_t total = (size_t) count * dim_count;
+    if (!table.empty())
+    {
+        CK(cudaMalloc(&d_table, table.size() * sizeof(uint32_t)));
+        CK(cudaMalloc(&d_offset, offset.size() * sizeof(uint32_t)));
+        CK(cudaMemcpyAsync(d_table, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
+        CK(cudaMemcpyAsync(d_offset, offset.data(), offset.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
+    }
+    CK(cudaMalloc(&d_out, total * sizeof(double)));
+    launch_qmc_sequence(kind, scramble, n_begin, count, dim_begin, dim_count, num_smp, bits, d_table, d_offset, n_primes,
+                        d_out, d.stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, total * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    cudaFree(d_table); cudaFree(d_offset); cudaFree(d_out);
+    return 0;
+}
+
+int cuda_trace_qmc_cranley_patterson(cuda_trace_ctx *ctx, const double *x, double e, uint32_t count, double *out)
+{
+    if (!ctx || (count && (!x || !out)))
+        return CUDA_TRACE_ERR_ARG;
+    if (count == 0)
+        return 0;
+    DeviceState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.ordinal));
+    double *d_x = nullptr, *d_o = nullptr;
+    CK(cudaMalloc(&d_x, count * sizeof(double)));
+    CK(cudaMalloc(&d_o, count * sizeof(double)));
+    CK(cudaMemcpyAsync(d_x, x, count * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+    launch_cranley_patterson(d_x, e, count, d_o, d.stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_o, count * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    cudaFree(d_x); cudaFree(d_o);
     return 0;
 }
 

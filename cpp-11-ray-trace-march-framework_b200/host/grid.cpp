@@ -27,8 +27,12 @@ Grid::Grid(std::unique_ptr<Mesh> mesh, uint grid_res)
     : m_mesh(std::move(mesh)), m_cell_wdh(0.0f), m_inv_cell_wdh(0.0f), m_num_refs(0), m_ctx(nullptr)
 {
     m_grid_dim[0] = m_grid_dim[1] = m_grid_dim[2] = 0;
-    if (!m_mesh || m_mesh->m_vertices.empty() || m_mesh->m_triangles.empty() || grid_res == 0)
-        throw std::runtime_error("Grid: empty mesh or zero resolution"); // reference asserts (grid.cpp:15-16)
+    if (!m_mesh || m_mesh->m_vertices.empty() || m_mesh->m_triangles.empty())
+        throw std::runtime_error("Grid: empty mesh"); // reference asserts (grid.cpp:15)
+    if (grid_res == kAutoResolution)
+        grid_res = cuda_trace_suggest_grid_res(uint32(m_mesh->m_triangles.size()));
+    if (grid_res == 0)
+        throw std::runtime_error("Grid: zero resolution"); // reference asserts (grid.cpp:16)
 
     const double t0 = TimerGetTick();
     int rc = cuda_trace_init(GetDeviceCount(), &m_ctx);

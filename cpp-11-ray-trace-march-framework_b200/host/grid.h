@@ -17,7 +17,9 @@ struct cuda_trace_ctx;
 class Grid
 {
 public:
-    // Throws std::runtime_error if no CUDA device is usable or the build fails
+    // grid_res: cells along the longest axis (reference: always 64), or kAutoResolution for about
+    // three cells per triangle.  Throws std::runtime_error if no CUDA device is usable / the build fails
+    static const uint kAutoResolution = 0xFFFFFFFFu;
     Grid(std::unique_ptr<Mesh> mesh, uint grid_res);
     ~Grid();
     Grid(const Grid&) = delete;

@@ -121,6 +121,12 @@ int cuda_trace_set_shard_signals(cuda_trace_ctx *ctx, int enable);
 int cuda_trace_upload_scene(cuda_trace_ctx *ctx, const float *vertices, uint32_t num_vertices,
                             const uint32_t *triangles, uint32_t num_triangles, uint32_t grid_res);
 
+/* Grid density heuristic for cuda_trace_upload_scene (the reference hard-codes 64 cells on the longest
+ * axis, scene.cpp:7): about three cells per triangle, res = cbrt(3 T) clamped to [16, 640].  The
+ * density sweep on the 50 M-triangle soup (profiles/r01_c5_grid_density_sweep.txt) has its optimum
+ * at 512-640 where this gives 532; results stay bit-exact for ANY resolution (same algorithm). */
+uint32_t cuda_trace_suggest_grid_res(uint32_t num_triangles);
+
 /* Same, but with a grid supplied by the caller instead of built on the device (parity harness:
  * inject the reference's own grid).  cell_offset has desc->num_cells + 1 entries. */
 int cuda_trace_upload_scene_with_grid(cuda_trace_ctx *ctx, const float *vertices, uint32_t num_vertices,
@@ -167,6 +173,24 @@ int cuda_trace_intersect_rays(cuda_trace_ctx *ctx, uint32_t n, const float *orig
 
 /* The renderer.cpp:49-60 sample table as the device computes it: xy = spp x {x, y} */
 int cuda_trace_sample_table(cuda_trace_ctx *ctx, uint32_t spp, float *xy);
+
+/* ---- QMC sample tables on the device (the reference's sampling module, sampling.cpp:55-290) ------
+ * out[i * dim_count + j] = sequence(n_begin + i, dim_begin + j), fp64 like the reference.
+ *   kind:     0 HaltonSequence, 1 HammersleySequence(num_smp), 2 HaltonZarembaSequence,
+ *             3 HammersleyZarembaSequence(num_smp), 4 RadicalInverseBase2(n, bits),
+ *             5 SobolRadicalInverseBase2(n, bits), 6 LarcherPillichshammerRadicalInverseBase2(n, bits)
+ *   scramble (kinds 0, 1; sampling.h:37-95): 0 ScrambleNone, 2 ScrambleFaure (first 128 primes, generated
+ *             here), 3 ScrambleReverse (128 primes), 1 / 4 digit permutations supplied by the caller in
+ *             `perm` = the tables of the first `perm_primes` primes back to back (2 + 3 + 5 + ... entries):
+ *             1 for the Braaten-Weller table (16 primes; assets/sampling/braaten_weller_16.u32), 4 for any
+ *             other, e.g. the reference's ScrambleRandomized table, which is whatever the host's
+ *             std::random_shuffle produced (sampling.cpp:174-192) and must therefore be uploaded.
+ *   dim_begin + dim_count <= 1000 (PRIME_TBL_SIZE).  perm may be NULL for scramble 0, 2, 3. */
+int cuda_trace_qmc_sequence(cuda_trace_ctx *ctx, uint32_t kind, uint32_t scramble, const uint32_t *perm,
+                            uint32_t perm_primes, uint32_t n_begin, uint32_t count, uint32_t dim_begin,
+                            uint32_t dim_count, uint32_t num_smp, uint32_t bits, double *out);
+/* CranleyPattersonRotation(x[i], e) (sampling.cpp:283-290) */
+int cuda_trace_qmc_cranley_patterson(cuda_trace_ctx *ctx, const double *x, double e, uint32_t count, double *out);
 
 /* Optional instrumentation: count rays / visited cells / triangle tests / hits of the next frames
  * (slower kernel variant).  cuda_trace_get_counters returns those of the last frame. */

@@ -98,6 +98,34 @@ class Ref:
     def hardware_threads(self):
         return self.lib.ref_hardware_threads()
 
+    # -- the reference's sampling module (sampling.h / sampling.cpp)
+    def qmc_sequence(self, kind, scramble, n_begin, count, dim_begin=0, dim_count=1, num_smp=1, bits=0):
+        out = np.zeros((count, dim_count), np.float64)
+        self.lib.ref_qmc_sequence.argtypes = [C.c_uint32] * 8 + [C.POINTER(C.c_double)]
+        self.lib.ref_qmc_sequence(kind, scramble, n_begin, count, dim_begin, dim_count, num_smp, bits,
+                                  out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def qmc_tables(self, scramble, n_primes):
+        """Permutation tables of the first n_primes primes back to back (scramble 1 BW, 2 Faure, 3 reverse, 4 randomized)."""
+        self.lib.ref_qmc_table.restype = C.c_uint32
+        self.lib.ref_qmc_table.argtypes = [C.c_uint32, C.c_uint32, _U32P]
+        parts = []
+        for i in range(n_primes):
+            buf = np.zeros(8192, np.uint32)
+            n = self.lib.ref_qmc_table(scramble, i, _p(buf, _U32P))
+            parts.append(buf[:n].copy())
+        return np.concatenate(parts)
+
+    def qmc_prime(self, idx):
+        self.lib.ref_qmc_prime.restype = C.c_uint32
+        return int(self.lib.ref_qmc_prime(C.c_uint32(idx)))
+
+    def cranley_patterson(self, x, e):
+        self.lib.ref_qmc_cranley_patterson.restype = C.c_double
+        self.lib.ref_qmc_cranley_patterson.argtypes = [C.c_double, C.c_double]
+        return np.array([self.lib.ref_qmc_cranley_patterson(float(v), float(e)) for v in np.ravel(x)], np.float64)
+
     def sample_table(self, spp):
         xy = np.zeros((spp, 2), np.float32)
         self.lib.ref_sample_table(spp, _p(xy, _F32P))

@@ -482,6 +482,76 @@ int ref_tri_test(int variant, const float *o, const float *d, const float *v0, c
     return hit ? 1 : 0;
 }
 
+// ----------------------------------------------------------------------------- sampling module
+// kind: 0 Halton, 1 Hammersley, 2 HaltonZaremba, 3 HammersleyZaremba, 4 RadicalInverseBase2,
+//       5 SobolRadicalInverseBase2, 6 LarcherPillichshammerRadicalInverseBase2
+// scramble (kinds 0,1): 0 none, 1 Braaten-Weller, 2 Faure, 3 reverse, 4 randomized
+// out[i * dim_count + j] = sequence(n_begin + i, dim_begin + j)     (sampling.h:91-120, sampling.cpp:194-281)
+void ref_qmc_sequence(uint32 kind, uint32 scramble, uint32 n_begin, uint32 count, uint32 dim_begin,
+                      uint32 dim_count, uint32 num_smp, uint32 bits, double *out)
+{
+    static bool init = false;
+    if (!init)
+    {
+        SAMP::Initialize();
+        init = true;
+    }
+    for (uint32 i = 0; i < count; i++)
+        for (uint32 j = 0; j < dim_count; j++)
+        {
+            const uint32 n = n_begin + i, dim = dim_begin + j;
+            double v = 0.0;
+            switch (kind)
+            {
+                case 0:
+                    v = scramble == 0 ? SAMP::HaltonSequence<SAMP::ScrambleNone>(n, dim)
+                      : scramble == 1 ? SAMP::HaltonSequence<SAMP::ScrambleBraatenWeller>(n, dim)
+                      : scramble == 2 ? SAMP::HaltonSequence<SAMP::ScrambleFaure>(n, dim)
+                      : scramble == 3 ? SAMP::HaltonSequence<SAMP::ScrambleReverse>(n, dim)
+                      :                 SAMP::HaltonSequence<SAMP::ScrambleRandomized>(n, dim);
+                    break;
+                case 1:
+                    v = scramble == 0 ? SAMP::HammersleySequence<SAMP::ScrambleNone>(n, dim, num_smp)
+                      : scramble == 1 ? SAMP::HammersleySequence<SAMP::ScrambleBraatenWeller>(n, dim, num_smp)
+                      : scramble == 2 ? SAMP::HammersleySequence<SAMP::ScrambleFaure>(n, dim, num_smp)
+                      : scramble == 3 ? SAMP::HammersleySequence<SAMP::ScrambleReverse>(n, dim, num_smp)
+                      :                 SAMP::HammersleySequence<SAMP::ScrambleRandomized>(n, dim, num_smp);
+                    break;
+                case 2: v = SAMP::HaltonZarembaSequence(n, dim); break;
+                case 3: v = SAMP::HammersleyZarembaSequence(n, dim, num_smp); break;
+                case 4: v = SAMP::RadicalInverseBase2(n, bits); break;
+                case 5: v = SAMP::SobolRadicalInverseBase2(n, bits); break;
+                default: v = SAMP::LarcherPillichshammerRadicalInverseBase2(n, bits); break;
+            }
+            out[size_t(i) * dim_count + j] = v;
+        }
+}
+
+// Permutation table of one prime index: scramble 1 BW (16 primes), 2 Faure, 3 reverse, 4 randomized
+// (128 primes each).  Returns the table length (= the prime) or 0 if there is none.
+uint32 ref_qmc_table(uint32 scramble, uint32 prime_idx, uint32 *out)
+{
+    static bool init = false;
+    if (!init)
+    {
+        SAMP::Initialize();
+        init = true;
+    }
+    const std::vector<uint> *tbl = nullptr;
+    if (scramble == 1 && prime_idx < SAMP::BW_TBL_SIZE) tbl = &SAMP::g_braaten_weller_table[prime_idx];
+    if (scramble == 2 && prime_idx < SAMP::FAURE_TBL_SIZE) tbl = &SAMP::g_faure_table[prime_idx];
+    if (scramble == 3 && prime_idx < SAMP::REVERSE_TBL_SIZE) tbl = &SAMP::g_reverse_table[prime_idx];
+    if (scramble == 4 && prime_idx < SAMP::RANDOMIZED_TBL_SIZE) tbl = &SAMP::g_randomized_table[prime_idx];
+    if (!tbl)
+        return 0;
+    for (size_t i = 0; i < tbl->size(); i++)
+        out[i] = (*tbl)[i];
+    return uint32(tbl->size());
+}
+
+uint32 ref_qmc_prime(uint32 idx) { return idx < SAMP::PRIME_TBL_SIZE ? SAMP::g_prime_table[idx] : 0; }
+double ref_qmc_cranley_patterson(double x, double e) { return SAMP::CranleyPattersonRotation(x, e); }
+
 void ref_save_bmp(void *h, const char *filename)
 {
     StdoutToStderr quiet;
