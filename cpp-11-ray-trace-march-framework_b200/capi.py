@@ -64,6 +64,7 @@ SYMBOLS = {
     "cuda_trace_download_hits": (C.c_int, [C.c_void_p, _U32P, _F32P, _F32P, _F32P]),
     "cuda_trace_intersect_rays": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, C.c_uint32, _U32P, _F32P,
                                             _F32P, _F32P]),
+    "cuda_trace_intersect_rays_brute_force": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P, _F32P, _F32P]),
     "cuda_trace_sample_table": (C.c_int, [C.c_void_p, C.c_uint32, _F32P]),
     "cuda_trace_qmc_sequence": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _U32P, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]),
@@ -278,6 +279,16 @@ class CudaTrace:
                         np.empty(n, np.float32))
         self._ck(self.lib.cuda_trace_intersect_rays(self.h, n, _p(o, _F32P), _p(d, _F32P), variant,
                                                     _p(tri, _U32P), _p(t, _F32P), _p(u, _F32P), _p(v, _F32P)))
+        return tri, t, u, v
+
+    def intersect_rays_brute_force(self, origins, dirs):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = len(o)
+        tri, t, u, v = (np.empty(n, np.uint32), np.empty(n, np.float32), np.empty(n, np.float32),
+                        np.empty(n, np.float32))
+        self._ck(self.lib.cuda_trace_intersect_rays_brute_force(self.h, n, _p(o, _F32P), _p(d, _F32P), _p(tri, _U32P),
+                                                                _p(t, _F32P), _p(u, _F32P), _p(v, _F32P)))
         return tri, t, u, v
 
     def sample_table(self, spp):

@@ -1073,8 +1073,8 @@ int cuda_trace_download_hits(cuda_trace_ctx *ctx, uint32_t *tri_idx, float *t, f
     return 0;
 }
 
-int cuda_trace_intersect_rays(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs,
-                              uint32_t variant, uint32_t *tri_idx, float *t, float *u, float *v)
+static int intersect_rays_impl(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs, uint32_t variant,
+                               bool brute_force, uint32_t *tri_idx, float *t, float *u, float *v)
 {
     if (!ctx || (n && (!origins || !dirs || !tri_idx || !t || !u || !v)) || variant > 1)
         return CUDA_TRACE_ERR_ARG;
@@ -1094,7 +1094,10 @@ int cuda_trace_intersect_rays(cuda_trace_ctx *ctx, uint32_t n, const float *orig
     RayBatchParams p;
     p.grid = grid_dev(ctx, d);
     p.n = n; p.origins = d_o; p.dirs = d_d; p.tri = d_i; p.t = d_t; p.u = d_u; p.v = d_v;
-    launch_intersect_rays(p, variant, d.stream);
+    if (brute_force)
+        launch_brute_force(d.d_vtx, d.d_tri, ctx->num_tri, p, d.stream);
+    else
+        launch_intersect_rays(p, variant, d.stream);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(tri_idx, d_i, (size_t) n * 4, cudaMemcpyDeviceToHost, d.stream));
@@ -1104,6 +1107,18 @@ int cuda_trace_intersect_rays(cuda_trace_ctx *ctx, uint32_t n, const float *orig
     CK(cudaStreamSynchronize(d.stream));
     cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_u); cudaFree(d_v); cudaFree(d_i);
     return 0;
+}
+
+int cuda_trace_intersect_rays(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs,
+                              uint32_t variant, uint32_t *tri_idx, float *t, float *u, float *v)
+{
+    return intersect_rays_impl(ctx, n, origins, dirs, variant, false, tri_idx, t, u, v);
+}
+
+int cuda_trace_intersect_rays_brute_force(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs,
+                                          uint32_t *tri_idx, float *t, float *u, float *v)
+{
+    return intersect_rays_impl(ctx, n, origins, dirs, 0, true, tri_idx, t, u, v);
 }
 
 int cuda_trace_sample_table(cuda_trace_ctx *ctx, uint32_t spp, float *xy)

@@ -252,6 +252,37 @@ __global__ void __launch_bounds__(128) intersect_rays_kernel(const __grid_consta
     p.v[i] = is_hit ? hit.v : 0.0f;
 }
 
+// renderer.cpp:157-197: closest hit over ALL triangles in index order (strict "cur_t < t": first wins ties)
+__global__ void __launch_bounds__(128) brute_force_kernel(const float *__restrict__ vtx, const uint32_t *__restrict__ tri,
+                                                          uint32_t num_tri, const __grid_constant__ RayBatchParams p)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n)
+        return;
+    const float3 o = make_float3(p.origins[3 * (size_t) i], p.origins[3 * (size_t) i + 1], p.origins[3 * (size_t) i + 2]);
+    const float3 d = make_float3(p.dirs[3 * (size_t) i], p.dirs[3 * (size_t) i + 1], p.dirs[3 * (size_t) i + 2]);
+    float best_t = FLT_MAX, best_u = 0.0f, best_v = 0.0f;
+    uint32_t best = 0xFFFFFFFFu;
+    for (uint32_t k = 0; k < num_tri; k++)
+    {
+        const uint32_t *tr = tri + (size_t) k * 6;
+        const float *p0 = vtx + (size_t) tr[0] * 6, *p1 = vtx + (size_t) tr[1] * 6, *p2 = vtx + (size_t) tr[2] * 6;
+        const float4 a = make_float4(p0[0], p0[1], p0[2], 0.0f);
+        const float4 b = make_float4(p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2], 0.0f);
+        const float4 c = make_float4(p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2], 0.0f);
+        float ct, cu, cv;
+        if (ray_tri_mt(o, d, a, b, c, ct, cu, cv) && ct < best_t)
+        {
+            best_t = ct; best_u = cu; best_v = cv; best = k;
+        }
+    }
+    const bool hit = best_t != FLT_MAX; // renderer.cpp:196
+    p.tri[i] = hit ? best : 0xFFFFFFFFu;
+    p.t[i] = hit ? best_t : 0.0f;
+    p.u[i] = hit ? best_u : 0.0f;
+    p.v[i] = hit ? best_v : 0.0f;
+}
+
 // K2: renderer.cpp:49-60 -> smp[s] = (Hammersley(s,0,N) - 0.5f, Hammersley(s,1,N) - 0.5f) with
 // sampling.h:113-120 / sampling.cpp:194-210 in fp64 (dim 0: double(n)/double(N); dim 1: radical
 // inverse base 2), rounded to fp32 by the store.  No FMA: -fmad=false covers fp64 too.
@@ -369,6 +400,12 @@ void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, cudaStream
         intersect_rays_kernel<1><<<blocks, 128, 0, stream>>>(p);
     else
         intersect_rays_kernel<0><<<blocks, 128, 0, stream>>>(p);
+}
+
+void launch_brute_force(const float *vtx, const uint32_t *tri, uint32_t num_tri, const RayBatchParams& p, cudaStream_t stream)
+{
+    if (p.n)
+        brute_force_kernel<<<(p.n + 127) / 128, 128, 0, stream>>>(vtx, tri, num_tri, p);
 }
 
 void launch_sample_table(float2 *smp, uint32_t spp, cudaStream_t stream)

@@ -171,6 +171,13 @@ int cuda_trace_download_hits(cuda_trace_ctx *ctx, uint32_t *tri_idx, float *t, f
 int cuda_trace_intersect_rays(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs,
                               uint32_t variant, uint32_t *tri_idx, float *t, float *u, float *v);
 
+/* Renderer::IntersectBruteForce (renderer.cpp:157-197): the same ray/triangle test against EVERY triangle,
+ * no grid -- the reference author's own cross-check of Grid::Intersect, kept as an on-device self-check.
+ * It differs from the grid result only where the grid's "hit must lie in the current cell" rule or an
+ * exact-t tie decides.  O(n * T): meant for small scenes / few rays. */
+int cuda_trace_intersect_rays_brute_force(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs,
+                                          uint32_t *tri_idx, float *t, float *u, float *v);
+
 /* The renderer.cpp:49-60 sample table as the device computes it: xy = spp x {x, y} */
 int cuda_trace_sample_table(cuda_trace_ctx *ctx, uint32_t spp, float *xy);
 

@@ -381,6 +381,23 @@ void ref_intersect_rays(void *h, uint32 n, const float *origins, const float *di
     }
 }
 
+// Renderer::IntersectBruteForce (renderer.cpp:157-197): the author's own cross-check of the grid
+void ref_intersect_rays_brute_force(void *h, uint32 n, const float *origins, const float *dirs,
+                                    uint32 *tri_idx, float *t_out, float *u_out, float *v_out)
+{
+    Renderer *r = static_cast<RefRenderer *>(h)->renderer.get();
+    for (uint32 i = 0; i < n; i++)
+    {
+        float t = 0.0f, u = 0.0f, v = 0.0f;
+        uint32 idx = 0xFFFFFFFFu;
+        const bool hit = r->IntersectBruteForce(Vec3f(origins + 3 * i), Vec3f(dirs + 3 * i), t, u, v, idx);
+        tri_idx[i] = hit ? idx : 0xFFFFFFFFu;
+        t_out[i] = hit ? t : 0.0f;
+        u_out[i] = hit ? u : 0.0f;
+        v_out[i] = hit ? v : 0.0f;
+    }
+}
+
 // Primary rays exactly as RenderTile generates them (for ray-generation parity)
 void ref_generate_rays(void *h, uint32 width, uint32 height, uint32 spp, uint32 y_begin,
                        uint32 y_end, float *origins, float *dirs)

@@ -175,6 +175,48 @@ def test_arbitrary_rays(cuda_trace, port, scene_data):
         assert (tri != 0xFFFFFFFF).sum() > 1000
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+@pytest.mark.parametrize("name,spp", [("killeroo", 4), ("room", 16), ("cornell", 1)])
+def test_occupancy_map_modes(cuda_trace, port, scene_data, monkeypatch, mode, name, spp):
+    """The three homes of the padded occupancy map (bits through L1 / bits in shared memory / one byte
+    per cell in shared memory with the DDA tracking the byte address) and both phase-A forms must give
+    the same bits.  Small frames default to mode 0, so the shared-memory modes are forced here."""
+    monkeypatch.setenv("RTM_OCC_MODE", mode)
+    monkeypatch.setenv("RTM_THREADS", "1024" if mode != "0" else "256")
+    sd = scene_data(name)
+    w, h = 256, 144
+    cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
+    f = frame_for(cuda_trace, port, sd, w, h, spp, keep_hits=True)
+    img = cuda_trace.trace_tiles(f)
+    tri, t, u, v = cuda_trace.download_hits(w, h, spp)
+    o = port.scene(sd.vtx, sd.tri, 64).render(sd.cam16, sd.fov, w, h, spp, want_hits=True, want_tuv=True)
+    assert np.array_equal(tri, o["tri"]) and np.array_equal(img, o["bgra"])
+    assert np.array_equal(t.view(np.uint32), o["t"].view(np.uint32))
+    # and the plain (non-instrumented) kernel instantiation
+    f2 = frame_for(cuda_trace, port, sd, w, h, spp)
+    assert np.array_equal(cuda_trace.trace_tiles(f2), o["bgra"])
+
+
+def test_brute_force_self_check(cuda_trace, ref, port, scene_data):
+    """Renderer::IntersectBruteForce on the device: bit-exact against the reference's own brute force, and
+    -- the author's cross-check -- equal to the grid result except where the grid's in-cell rule decides."""
+    sd = scene_data("cornell")
+    scenes = pkg("scenes")
+    m, fov, cam = scenes.build(ref.api, "cornell")
+    r = ref.renderer(m, fov, cam)
+    cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
+    o3, d3 = r.generate_rays(96, 64, 2, 0, 64)
+    o, d = o3.reshape(-1, 3), d3.reshape(-1, 3)
+    bt = cuda_trace.intersect_rays_brute_force(o, d)
+    rt = r.intersect_rays_brute_force(o, d)
+    assert np.array_equal(bt[0], rt[0])
+    for i in (1, 2, 3):
+        assert np.array_equal(bt[i].view(np.uint32), rt[i].view(np.uint32))
+    gt = cuda_trace.intersect_rays(o, d, 0)
+    assert (gt[0] != bt[0]).mean() < 0.01  # grid vs brute force: only boundary / tie cases differ
+    assert (bt[0] != 0xFFFFFFFF).sum() > 1000
+
+
 def test_counters_match_oracle(cuda_trace, port, scene_data):
     sd = scene_data("killeroo")
     w, h, spp = 160, 90, 4

@@ -31,7 +31,9 @@ CASES += [("cornell", 512, 512, 1, 64),          # BASELINE config C1, full size
           ("torusknot", 240, 135, 16, 64),        # C3 scaled
           ("room", 240, 135, 16, 64),             # C4 scaled
           ("tiger_soup_small", 160, 90, 4, 48),   # C5 construction at test size
-          ("killeroo", 97, 61, 3, 33)]            # odd everything
+          ("killeroo", 97, 61, 3, 33),            # odd everything
+          ("killeroo", 1920, 1080, 4, 64),        # BASELINE config C2, FULL size
+          ("torusknot", 1920, 1080, 16, 64)]      # BASELINE config C3, FULL size
 
 
 def md5(a):
