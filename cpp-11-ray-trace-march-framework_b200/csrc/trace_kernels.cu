@@ -48,20 +48,16 @@ __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const void 
     return rgb;
 }
 
-// All lanes call this; lane 0 adds `count` to the band's completion counter with release semantics
-__device__ __forceinline__ void publish_band(const TraceParams& p, uint32_t lane, uint32_t band, uint32_t count)
+// Adds `count` to a band's completion counter with release semantics (called by lane 0 after a warp barrier)
+__device__ __forceinline__ void release_add(const TraceParams& p, uint32_t band, uint32_t count)
 {
-    __syncwarp();
-    if (lane == 0)
-    {
-        if (p.band_scope_sys)
-            asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(count) : "memory");
-        else
-            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(count) : "memory");
-    }
+    if (p.band_scope_sys)
+        asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(count) : "memory");
+    else
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(count) : "memory");
 }
 
-template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE, bool RCP_GUARD>
+template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE, bool RCP_GUARD, bool BANDS>
 __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __grid_constant__ TraceParams p)
 {
     // shared memory: [sample table (renderer.cpp:49-60), spp x float2]
@@ -95,19 +91,25 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         // dynamic strip scheduler: one atomic per strip per warp
         // A cancelled frame still walks its strip list -- without tracing -- so that the per-band
         // completion counts the read-back waits on are reached (framebuffer.h:32 m_threads_stop)
-        uint32_t visit = 0, cancelled = 0;
+        uint32_t visit = 0;
+        bool cancel_seen = false;
         if (lane == 0)
         {
-            cancelled = *(volatile const uint32_t *) p.cancel;
+            cancel_seen = *(volatile const uint32_t *) p.cancel != 0;
             visit = atomicAdd(p.strip_counter, 1u);
         }
         visit = __shfl_sync(kFull, visit, 0);
-        cancelled = __shfl_sync(kFull, cancelled, 0);
-        if (visit >= p.shard_strips || (cancelled && !p.band_done))
+        // a VOTE result is warp-uniform by construction, which lets the compiler keep the traversal
+        // below free of divergence checks around its own votes
+        const bool cancelled = __any_sync(kFull, cancel_seen);
+        if (__any_sync(kFull, visit >= p.shard_strips) || (cancelled && !(BANDS && p.band_done)))
             break;
         // `fetch` = index of the strip within this shard, taken through the cost order of the
         // previous frame when there is one (schedule.cu)
-        const uint32_t fetch = p.fetch_order ? __ldg(&p.fetch_order[visit]) : visit;
+        // (broadcast through a shuffle: a loaded value is not provably warp-uniform, and everything
+        // derived from it -- strip, rectangle, loop bounds -- would make the compiler guard the
+        // traversal's votes with divergence checks: +3 instructions per triangle test)
+        const uint32_t fetch = __shfl_sync(kFull, p.fetch_order ? __ldg(&p.fetch_order[visit]) : visit, 0);
         const long long t_begin = p.strip_cycles ? clock64() : 0;
         const uint32_t slot_begin = 0, slot_end = slots;
         // the n-th strip of this shard: strips are dealt out in chunks of p.shard_chunk consecutive
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         const uint64_t chunk_id = (uint64_t) my_chunk * p.shard_world +
                                   (p.shard_rank + p.shard_world - my_chunk % p.shard_world) % p.shard_world;
         const uint64_t strip64 = chunk_id * p.shard_chunk + in_chunk;
-        if (strip64 >= p.total_strips)
+        if (__any_sync(kFull, strip64 >= p.total_strips)) // (votes keep these branches provably warp-uniform)
             continue;
         const uint32_t strip = (uint32_t) strip64;
 
@@ -175,19 +177,19 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         }
         else
         {
-            // one pixel at a time, 32 samples per round
+            // one pixel at a time, 32 samples per round.  (No `continue` in this loop: with one the
+            // compiler treats the whole strip loop as possibly divergent and guards every vote.)
             for (uint32_t slot = slot_begin; slot < slot_end; slot++)
             {
                 const uint32_t ox = (slot & 1u) | ((slot >> 1) & 2u) | ((slot >> 2) & 4u);
                 const uint32_t oy = ((slot >> 1) & 1u) | ((slot >> 2) & 2u);
-                if (ox >= bw || oy >= bh)
-                    continue;
+                const bool inside = ox < bw && oy < bh; // clipped strips: the pixel lies outside the tile
                 const uint32_t px = bx0 + ox, py = by0 + oy;
                 float3 acc = make_float3(0.0f, 0.0f, 0.0f);
                 for (uint32_t sb = 0; sb < p.spp; sb += 32)
                 {
                     const uint32_t s = sb + lane;
-                    const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_MODE, RCP_GUARD>(p, s_occ, s < p.spp, px, py, s, s_smp, &cnt);
+                    const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_MODE, RCP_GUARD>(p, s_occ, inside && s < p.spp, px, py, s, s_smp, &cnt);
                     const uint32_t n = min(32u, p.spp - sb);
                     for (uint32_t k = 0; k < n; k++)
                     {
@@ -196,13 +198,13 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
                         acc.z += __shfl_sync(kFull, rgb.z, (int) k);
                     }
                 }
-                if (lane == 0)
+                if (inside && lane == 0)
                     p.framebuffer[(size_t) py * p.width + px] = resolve_pixel(acc, spp_f, p.gamma != 0);
             }
         }
-        if (p.strip_cycles && lane == 0)
-            p.strip_cycles[fetch] = (uint32_t) min(clock64() - t_begin, 0x7FFFFFFFll);
-        if (p.band_done)
+        // (compiled out of the BANDS == false instantiation: the warp barrier in here makes the compiler
+        // guard every vote of the traversal with a divergence check, +3 instructions per triangle test)
+        if (BANDS && p.band_done)
         {
             // Publish "these strips' pixels are stored" per row band.  Finished strips are batched
             // per warp (same band, up to 8) because the publication is a release: a warp barrier
@@ -211,19 +213,28 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
             // The host's copy stream waits on these counters and ships each row band to the host
             // while later bands are still being traced.
             const uint32_t b0 = by0 / p.band_rows, b1 = (by0 + bh - 1) / p.band_rows;
-            if (pend_count && (pend_band != b0 || pend_count >= 8u))
+            const bool flush = pend_count && (pend_band != b0 || pend_count >= 8u);
+            __syncwarp(); // unconditional, at the top level of the strip loop (a barrier under a
+                          // data-dependent branch would make the compiler guard every vote in the loop)
+            if (lane == 0)
             {
-                publish_band(p, lane, pend_band, pend_count);
-                pend_count = 0;
+                if (flush)
+                    release_add(p, pend_band, pend_count);
+                if (b1 != b0)
+                    release_add(p, b1, 1u); // a strip straddling two bands counts in both
             }
+            if (flush)
+                pend_count = 0;
             pend_band = b0;
             pend_count++;
-            if (b1 != b0)
-                publish_band(p, lane, b1, 1u); // a strip straddling two bands counts in both
         }
     }
-    if (p.band_done && pend_count)
-        publish_band(p, lane, pend_band, pend_count);
+    if (BANDS && p.band_done)
+    {
+        __syncwarp();
+        if (lane == 0 && pend_count)
+            release_add(p, pend_band, pend_count);
+    }
 
     if (COUNT)
     {
@@ -303,24 +314,29 @@ __global__ void sample_table_kernel(float2 *smp, uint32_t spp)
     smp[s] = make_float2((float) (x - 0.5), (float) (val - 0.5));
 }
 
-// The rcp range guard (scenes larger than 1e14 units) is only instantiated for the plain kernel;
-// the instrumented variants always keep it.
+// The plain kernel exists with / without the rcp range guard (scenes larger than 1e14 units) and
+// with / without the row-band completion counters; the instrumented variants always carry both.
+template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE, bool RCP_GUARD, bool BANDS>
+void launch_instance(const TraceParams& p, int grid_blocks, int threads, size_t smem, cudaStream_t stream)
+{
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, RCP_GUARD, BANDS>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, RCP_GUARD, BANDS><<<grid_blocks, threads, smem, stream>>>(p);
+}
+
 template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE>
 void launch_mode(const TraceParams& p, int grid_blocks, int threads, size_t smem, cudaStream_t stream)
 {
     constexpr bool kPlain = !KEEP_HITS && !COUNT;
-    if (kPlain && !p.rcp_guard)
+    if (kPlain)
     {
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, !kPlain>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, !kPlain><<<grid_blocks, threads, smem, stream>>>(p);
-        return;
+        const bool guard = p.rcp_guard != 0, bands = p.band_done != nullptr;
+        if (!guard && !bands) return launch_instance<VARIANT, KEEP_HITS, COUNT, OCC_MODE, !kPlain, !kPlain>(p, grid_blocks, threads, smem, stream);
+        if (!guard && bands)  return launch_instance<VARIANT, KEEP_HITS, COUNT, OCC_MODE, !kPlain, true>(p, grid_blocks, threads, smem, stream);
+        if (guard && !bands)  return launch_instance<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true, !kPlain>(p, grid_blocks, threads, smem, stream);
     }
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true><<<grid_blocks, threads, smem, stream>>>(p);
+    launch_instance<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true, true>(p, grid_blocks, threads, smem, stream);
 }
 
 template <int VARIANT, bool KEEP_HITS, bool COUNT>
@@ -340,9 +356,9 @@ int occupancy_mode(int threads, size_t smem)
 {
     int n = 0;
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true>,
+        cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true>, threads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true, true>, threads, smem);
     return n;
 }
 
