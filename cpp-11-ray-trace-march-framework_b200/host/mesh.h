@@ -35,7 +35,7 @@ struct Mesh
     bool Read(const char *filename, bool flip_winding = false);
     void CornellBox();
 
-    // Additions (not in the reference): the binary asset format of tools/convert_meshes.py --
+    // Additions (not in the reference): the binary asset format of oracle/convert_meshes.py --
     // the state of a Mesh right after Read() -- and direct array access for the C wrappers
     bool ReadBinary(const char *filename);
     void SetArrays(const float *vtx6, uint32 num_vtx, const uint32 *tri6, uint32 num_tri);

@@ -29,7 +29,7 @@ def load_meshbin(name, flip_winding=False):
     """Read assets/meshes/<name>[.flip].meshbin -> (vtx float32 [V,6], tri uint32 [T,6]).
 
     The file is the state of the reference's ``Mesh`` right after ``Mesh::Read``
-    (tools/convert_meshes.py documents the layout)."""
+    (oracle/convert_meshes.py documents the layout)."""
     path = os.path.join(ASSET_DIR, name + (".flip" if flip_winding else "") + ".meshbin")
     with open(path, "rb") as f:
         data = f.read()

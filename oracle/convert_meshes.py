@@ -12,7 +12,7 @@ num_vertices x {float32 px,py,pz,nx,ny,nz}   (= Mesh::Vertex,   mesh.h:20-24, 24
 num_triangles x {uint32 v0,v1,v2, float32 nx,ny,nz} (= Mesh::Triangle, mesh.h:12-18, 24 B)
 
 `table_chair` is also stored with flip_winding=true (scene 3, application.cpp:352).
-Run:  python tools/convert_meshes.py        (needs `make -C oracle ref` first)
+Run:  python oracle/convert_meshes.py        (needs `make -C oracle ref` first)
 """
 import ctypes as C
 import os

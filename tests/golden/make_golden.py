@@ -8,7 +8,7 @@ triangle indices and of t/u/v (reference GenerateRay + Grid::Intersect), hit cou
 digest (dims, cell width bits, md5 of offsets / triangle lists).  One small case is stored in full
 (cornell 48x48x2: image + hit indices) so a failure can be localised.
 
-    python tools/make_golden.py      ->  tests/golden/ref_digests.json, tests/golden/cornell_48x48x2.npz
+    python tests/golden/make_golden.py      ->  tests/golden/ref_digests.json, tests/golden/cornell_48x48x2.npz
 """
 import hashlib
 import importlib
@@ -18,7 +18,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import pyoracle as po  # noqa: E402
 

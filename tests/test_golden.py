@@ -1,4 +1,4 @@
-"""Golden vectors generated from the unmodified reference (tools/make_golden.py): the oracle port
+"""Golden vectors generated from the unmodified reference (tests/golden/make_golden.py): the oracle port
 (CPU test) and the CUDA path (GPU test) must reproduce every digest.  These are the fixtures that
 still pin parity on a box where oracle/_ref is absent."""
 import hashlib

@@ -14,12 +14,13 @@ host = hostapi.host_api()
 m, fov, cam = scenes.build(host, scene)
 vtx, tri = m.arrays()
 group = mr.RankGroup(dist, "cuda")
-for share in (False, True):
+for share, signals in ((False, False), (True, False), (True, True)):
     ct = capi.CudaTrace(devices=[local])
     ct.upload_scene(vtx, tri, res)
     ct.set_shard(rank, world)
     if share:
         mr.share_framebuffer(ct, group, w, h)
+    ct.set_shard_signals(signals)
     fov_xs, aspect = host.camera_constants(fov, w, h)
     frame = ct.make_frame(w, h, spp, cam, fov_xs, aspect)
     ms = []
@@ -30,7 +31,7 @@ for share in (False, True):
         ms.append(ct.last_kernel_ms())
     allms = group.allreduce_sum(np.eye(world)[rank] * np.median(ms[3:]))
     if rank == 0:
-        print(wl, "shared_fb" if share else "local_fb", "per-rank kernel ms:", np.round(allms, 3).tolist(), flush=True)
+        print(wl, "shared_fb" if share else "local_fb", "signals" if signals else "no-signals", "per-rank kernel ms:", np.round(allms, 3).tolist(), flush=True)
     group.barrier()
     ct.close()
 dist.destroy_process_group()
