@@ -65,6 +65,7 @@ SYMBOLS = {
     "cuda_trace_intersect_rays": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, C.c_uint32, _U32P, _F32P,
                                             _F32P, _F32P]),
     "cuda_trace_intersect_rays_brute_force": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P, _F32P, _F32P]),
+    "cuda_trace_ray_march": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P]),
     "cuda_trace_sample_table": (C.c_int, [C.c_void_p, C.c_uint32, _F32P]),
     "cuda_trace_qmc_sequence": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _U32P, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]),
@@ -290,6 +291,14 @@ class CudaTrace:
         self._ck(self.lib.cuda_trace_intersect_rays_brute_force(self.h, n, _p(o, _F32P), _p(d, _F32P), _p(tri, _U32P),
                                                                 _p(t, _F32P), _p(u, _F32P), _p(v, _F32P)))
         return tri, t, u, v
+
+    def ray_march(self, origins, dirs):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = len(o)
+        hit, t = np.empty(n, np.uint32), np.empty(n, np.float32)
+        self._ck(self.lib.cuda_trace_ray_march(self.h, n, _p(o, _F32P), _p(d, _F32P), _p(hit, _U32P), _p(t, _F32P)))
+        return hit, t
 
     def sample_table(self, spp):
         xy = np.zeros((spp, 2), np.float32)

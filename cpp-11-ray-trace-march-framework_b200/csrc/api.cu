@@ -1121,6 +1121,32 @@ int cuda_trace_intersect_rays_brute_force(cuda_trace_ctx *ctx, uint32_t n, const
     return intersect_rays_impl(ctx, n, origins, dirs, 0, true, tri_idx, t, u, v);
 }
 
+int cuda_trace_ray_march(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs, uint32_t *hit, float *t)
+{
+    if (!ctx || (n && (!origins || !dirs || !hit || !t)))
+        return CUDA_TRACE_ERR_ARG;
+    if (!ctx->have_scene)
+        return fail(ctx, CUDA_TRACE_ERR_NO_SCENE, "ray_march: upload a scene first");
+    if (n == 0)
+        return 0;
+    DeviceState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.ordinal));
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
+    uint32_t *d_h = nullptr;
+    CK(cudaMalloc(&d_o, (size_t) n * 12)); CK(cudaMalloc(&d_d, (size_t) n * 12));
+    CK(cudaMalloc(&d_t, (size_t) n * 4)); CK(cudaMalloc(&d_h, (size_t) n * 4));
+    CK(cudaMemcpyAsync(d_o, origins, (size_t) n * 12, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d_d, dirs, (size_t) n * 12, cudaMemcpyHostToDevice, d.stream));
+    launch_ray_march(d.d_vtx, d.d_tri, ctx->num_tri, n, d_o, d_d, d_h, d_t, d.stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hit, d_h, (size_t) n * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(t, d_t, (size_t) n * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_h);
+    return 0;
+}
+
 int cuda_trace_sample_table(cuda_trace_ctx *ctx, uint32_t spp, float *xy)
 {
     if (!ctx || !xy || spp == 0)

@@ -294,6 +294,75 @@ __global__ void __launch_bounds__(128) brute_force_kernel(const float *__restric
     p.v[i] = hit ? best_v : 0.0f;
 }
 
+// triangle.h:172-181: squared distance from p to the segment a-b
+__device__ __forceinline__ float seg_dist_sq(const float a[3], const float b[3], const float p[3])
+{
+    const float abx = b[0] - a[0], aby = b[1] - a[1], abz = b[2] - a[2];
+    const float len_sq = dot_ref(abx, aby, abz, abx, aby, abz);
+    float t = dot_ref(p[0] - a[0], p[1] - a[1], p[2] - a[2], abx, aby, abz) / len_sq;
+    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t); // Clamp (lin_alg.h:205-212)
+    const float qx = p[0] - (a[0] + abx * t), qy = p[1] - (a[1] + aby * t), qz = p[2] - (a[2] + abz * t);
+    return dot_ref(qx, qy, qz, qx, qy, qz);
+}
+
+// triangle.h:183-198 DistancePointTri = ComputeBarycentric (:133-156) then plane distance or nearest edge
+__device__ float point_tri_distance(const float p[3], const float v0[3], const float v1[3], const float v2[3])
+{
+    const float e0x = v2[0] - v0[0], e0y = v2[1] - v0[1], e0z = v2[2] - v0[2];
+    const float e1x = v1[0] - v0[0], e1y = v1[1] - v0[1], e1z = v1[2] - v0[2];
+    const float e2x = p[0] - v0[0], e2y = p[1] - v0[1], e2z = p[2] - v0[2];
+    const float d00 = dot_ref(e0x, e0y, e0z, e0x, e0y, e0z), d01 = dot_ref(e0x, e0y, e0z, e1x, e1y, e1z);
+    const float d02 = dot_ref(e0x, e0y, e0z, e2x, e2y, e2z), d11 = dot_ref(e1x, e1y, e1z, e1x, e1y, e1z);
+    const float d12 = dot_ref(e1x, e1y, e1z, e2x, e2y, e2z);
+    const float inv_denom = 1.0f / (d00 * d11 - d01 * d01);
+    const float u = (d00 * d12 - d01 * d02) * inv_denom, v = (d11 * d02 - d01 * d12) * inv_denom;
+    if ((u >= 0.0f) && (v >= 0.0f) && (u + v < 1.0f))
+    {
+        const float w = 1.0f - u - v; // BarycentricInterpolate(u, v, v0, v1, v2) (triangle.h:158-161)
+        const float qx = p[0] - (v1[0] * u + v2[0] * v + v0[0] * w);
+        const float qy = p[1] - (v1[1] * u + v2[1] * v + v0[1] * w);
+        const float qz = p[2] - (v1[2] * u + v2[2] * v + v0[2] * w);
+        return sqrtf(dot_ref(qx, qy, qz, qx, qy, qz));
+    }
+    const float a = seg_dist_sq(v0, v1, p), b = seg_dist_sq(v0, v2, p), c = seg_dist_sq(v1, v2, p);
+    const float bc = (c < b) ? c : b; // std::min(b, c)
+    return sqrtf((bc < a) ? bc : a);  // std::min(a, min(b, c))
+}
+
+// renderer.cpp:24-41 (RayMarch) over renderer.cpp:138-155 (DistanceBruteForce)
+__global__ void __launch_bounds__(128) ray_march_kernel(const float *__restrict__ vtx, const uint32_t *__restrict__ tri,
+                                                        uint32_t num_tri, uint32_t n, const float *__restrict__ origins,
+                                                        const float *__restrict__ dirs, uint32_t *__restrict__ hit_out,
+                                                        float *__restrict__ t_out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float o[3] = { origins[3 * (size_t) i], origins[3 * (size_t) i + 1], origins[3 * (size_t) i + 2] };
+    const float d[3] = { dirs[3 * (size_t) i], dirs[3 * (size_t) i + 1], dirs[3 * (size_t) i + 2] };
+    float t = 0.0f;
+    uint32_t hit = 0;
+    for (uint32_t step = 0; step < 128u; step++)
+    {
+        const float pos[3] = { o[0] + d[0] * t, o[1] + d[1] * t, o[2] + d[2] * t };
+        float dist = FLT_MAX;
+        for (uint32_t k = 0; k < num_tri; k++)
+        {
+            const uint32_t *tr = tri + (size_t) k * 6;
+            const float dk = point_tri_distance(pos, vtx + (size_t) tr[0] * 6, vtx + (size_t) tr[1] * 6, vtx + (size_t) tr[2] * 6);
+            dist = (dk < dist) ? dk : dist; // std::min(dist, dk)
+        }
+        t += dist;
+        if (dist < 0.001f)
+        {
+            hit = 1;
+            break;
+        }
+    }
+    hit_out[i] = hit;
+    t_out[i] = t;
+}
+
 // K2: renderer.cpp:49-60 -> smp[s] = (Hammersley(s,0,N) - 0.5f, Hammersley(s,1,N) - 0.5f) with
 // sampling.h:113-120 / sampling.cpp:194-210 in fp64 (dim 0: double(n)/double(N); dim 1: radical
 // inverse base 2), rounded to fp32 by the store.  No FMA: -fmad=false covers fp64 too.
@@ -422,6 +491,13 @@ void launch_brute_force(const float *vtx, const uint32_t *tri, uint32_t num_tri,
 {
     if (p.n)
         brute_force_kernel<<<(p.n + 127) / 128, 128, 0, stream>>>(vtx, tri, num_tri, p);
+}
+
+void launch_ray_march(const float *vtx, const uint32_t *tri, uint32_t num_tri, uint32_t n, const float *origins,
+                      const float *dirs, uint32_t *hit, float *t, cudaStream_t stream)
+{
+    if (n)
+        ray_march_kernel<<<(n + 127) / 128, 128, 0, stream>>>(vtx, tri, num_tri, n, origins, dirs, hit, t);
 }
 
 void launch_sample_table(float2 *smp, uint32_t spp, cudaStream_t stream)

@@ -78,6 +78,8 @@ int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count, 
 size_t trace_tiles_smem_bytes(uint32_t spp, uint32_t occ_smem_words);
 void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, cudaStream_t stream);
 void launch_sample_table(float2 *smp, uint32_t spp, cudaStream_t stream);
+void launch_ray_march(const float *vtx, const uint32_t *tri, uint32_t num_tri, uint32_t n, const float *origins,
+                      const float *dirs, uint32_t *hit, float *t, cudaStream_t stream);
 void launch_brute_force(const float *vtx, const uint32_t *tri, uint32_t num_tri, const RayBatchParams& p, cudaStream_t stream);
 
 // cost-ordered scheduling (schedule.cu): 4 kernels; scratch = 2 * ceil(n / 1024) + 2 words

@@ -192,6 +192,10 @@ int rtm_renderer_intersect(void *h, const float *origin, const float *dir, float
         return -1;
     }
 }
+int rtm_renderer_ray_march(void *h, const float *origin, const float *dir, float *t)
+{
+    return static_cast<HostRenderer *>(h)->renderer->RayMarch(Vec3f(origin), Vec3f(dir), *t) ? 1 : 0;
+}
 void rtm_renderer_grid_info(void *h, uint32 *dim, float *aabb_min, float *aabb_max, float *cell_wdh, uint64 *refs)
 {
     const Grid *g = static_cast<HostRenderer *>(h)->renderer->GetScene()->GetGrid();

@@ -86,3 +86,12 @@ void Renderer::RenderTiles(Tile * const *tiles, uint count)
             std::memcpy(dst + size_t(y) * tw, &m_frame[rects[i].x0 + size_t(rects[i].y0 + y) * m_width], size_t(tw) * 4);
     }
 }
+
+bool Renderer::RayMarch(Vec3f origin, Vec3f dir, float& t)
+{
+    const float o[3] = { origin.x, origin.y, origin.z }, d[3] = { dir.x, dir.y, dir.z };
+    uint32 hit = 0;
+    if (cuda_trace_ray_march(m_scene->GetGrid()->GetDeviceContext(), 1, o, d, &hit, &t) != 0)
+        return false;
+    return hit != 0;
+}

@@ -28,6 +28,9 @@ public:
     void SetGammaCorrection(bool on) { m_gamma = on; }
     Scene * GetScene() { return m_scene.get(); }
     float GetLastKernelMilliseconds() const { return m_last_kernel_ms; }
+    // The reference's sphere tracer (renderer.h:21 / renderer.cpp:24-41; protected and unused there): a one-ray
+    // GPU query through cuda_trace_ray_march.
+    bool RayMarch(Vec3f origin, Vec3f dir, float& t);
 
 protected:
     void RenderTile(Tile& tile) override;

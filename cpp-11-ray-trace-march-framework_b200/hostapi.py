@@ -42,6 +42,8 @@ def load_host_library():
         lib.rtm_renderer_device_context.argtypes = [C.c_void_p]
         lib.rtm_renderer_intersect.restype = C.c_int
         lib.rtm_renderer_intersect.argtypes = [C.c_void_p, _F32P, _F32P, _F32P, _U32P]
+        lib.rtm_renderer_ray_march.restype = C.c_int
+        lib.rtm_renderer_ray_march.argtypes = [C.c_void_p, _F32P, _F32P, _F32P]
         lib.rtm_renderer_grid_info.argtypes = [C.c_void_p, _U32P, _F32P, _F32P, _F32P, C.POINTER(C.c_uint64)]
         _lib = lib
     return _lib
@@ -99,6 +101,14 @@ class HostRenderer:
         if rc < 0:
             raise RuntimeError(self.lib.rtm_last_error().decode())
         return bool(rc), tuv, idx.value
+
+    def ray_march(self, origin, direction):
+        """Renderer::RayMarch (renderer.cpp:24-41) for one ray -> (hit, t)."""
+        o = np.ascontiguousarray(origin, np.float32)
+        d = np.ascontiguousarray(direction, np.float32)
+        t = C.c_float(0.0)
+        rc = self.lib.rtm_renderer_ray_march(self.h, o.ctypes.data_as(_F32P), d.ctypes.data_as(_F32P), C.byref(t))
+        return bool(rc), np.float32(t.value)
 
     def grid_info(self):
         dim = np.zeros(3, np.uint32)

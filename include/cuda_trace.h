@@ -178,6 +178,13 @@ int cuda_trace_intersect_rays(cuda_trace_ctx *ctx, uint32_t n, const float *orig
 int cuda_trace_intersect_rays_brute_force(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs,
                                           uint32_t *tri_idx, float *t, float *u, float *v);
 
+/* Renderer::RayMarch (renderer.cpp:24-41): sphere tracing -- up to 128 steps of t += DistanceBruteForce(pos)
+ * (renderer.cpp:138-155, DistancePointTri triangle.h:163-198) until the distance drops below 0.001.
+ * The "march" of the project's name; commented out of the reference's pixel loop, kept as a ray query.
+ * hit[i] = 1 / 0, t[i] = the parameter reached.  O(n * 128 * T): small scenes / few rays. */
+int cuda_trace_ray_march(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs, uint32_t *hit,
+                         float *t);
+
 /* The renderer.cpp:49-60 sample table as the device computes it: xy = spp x {x, y} */
 int cuda_trace_sample_table(cuda_trace_ctx *ctx, uint32_t spp, float *xy);
 

@@ -207,6 +207,15 @@ class RefRenderer:
                                                 _p(t, _F32P), _p(u, _F32P), _p(v, _F32P))
         return idx, t, u, v
 
+    def ray_march(self, origins, dirs):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = len(o)
+        hit, t = np.empty(n, np.uint32), np.empty(n, np.float32)
+        self.lib.ref_ray_march.argtypes = [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P]
+        self.lib.ref_ray_march(self.h, n, _p(o, _F32P), _p(d, _F32P), _p(hit, _U32P), _p(t, _F32P))
+        return hit, t
+
     def generate_rays(self, width, height, spp, y_begin, y_end):
         shape = (y_end - y_begin, width, spp, 3)
         o, d = np.empty(shape, np.float32), np.empty(shape, np.float32)

@@ -398,6 +398,18 @@ void ref_intersect_rays_brute_force(void *h, uint32 n, const float *origins, con
     }
 }
 
+// Renderer::RayMarch (renderer.cpp:24-41): sphere tracing against DistanceBruteForce (:138-155)
+void ref_ray_march(void *h, uint32 n, const float *origins, const float *dirs, uint32 *hit_out, float *t_out)
+{
+    Renderer *r = static_cast<RefRenderer *>(h)->renderer.get();
+    for (uint32 i = 0; i < n; i++)
+    {
+        float t = 0.0f;
+        hit_out[i] = r->RayMarch(Vec3f(origins + 3 * i), Vec3f(dirs + 3 * i), t) ? 1u : 0u;
+        t_out[i] = t;
+    }
+}
+
 // Primary rays exactly as RenderTile generates them (for ray-generation parity)
 void ref_generate_rays(void *h, uint32 width, uint32 height, uint32 spp, uint32 y_begin,
                        uint32 y_end, float *origins, float *dirs)

@@ -217,6 +217,22 @@ def test_brute_force_self_check(cuda_trace, ref, port, scene_data):
     assert (bt[0] != 0xFFFFFFFF).sum() > 1000
 
 
+def test_ray_march_matches_reference(cuda_trace, ref, scene_data):
+    """Renderer::RayMarch + DistanceBruteForce + DistancePointTri on the device, bit-exact (hit flag and the
+    parameter t reached) against the reference's own functions, on camera rays of the Cornell scene."""
+    sd = scene_data("cornell")
+    scenes = pkg("scenes")
+    m, fov, cam = scenes.build(ref.api, "cornell")
+    r = ref.renderer(m, fov, cam)
+    cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
+    o3, d3 = r.generate_rays(48, 32, 1, 0, 32)
+    o, d = o3.reshape(-1, 3), d3.reshape(-1, 3)
+    gh, gt = cuda_trace.ray_march(o, d)
+    rh, rt = r.ray_march(o, d)
+    assert np.array_equal(gh, rh) and np.array_equal(gt.view(np.uint32), rt.view(np.uint32))
+    assert 100 < int(gh.sum()) < len(gh)
+
+
 def test_counters_match_oracle(cuda_trace, port, scene_data):
     sd = scene_data("killeroo")
     w, h, spp = 160, 90, 4
