@@ -65,6 +65,7 @@ SYMBOLS = {
     "cuda_trace_intersect_rays": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, C.c_uint32, _U32P, _F32P,
                                             _F32P, _F32P]),
     "cuda_trace_intersect_rays_brute_force": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P, _F32P, _F32P]),
+    "cuda_trace_download_strip_cycles": (C.c_int, [C.c_void_p, _U32P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "cuda_trace_ray_march": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P]),
     "cuda_trace_sample_table": (C.c_int, [C.c_void_p, C.c_uint32, _F32P]),
     "cuda_trace_qmc_sequence": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _U32P, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -291,6 +292,15 @@ class CudaTrace:
         self._ck(self.lib.cuda_trace_intersect_rays_brute_force(self.h, n, _p(o, _F32P), _p(d, _F32P), _p(tri, _U32P),
                                                                 _p(t, _F32P), _p(u, _F32P), _p(v, _F32P)))
         return tri, t, u, v
+
+    def strip_cycles(self):
+        """SM cycles per strip of the last frame (this shard's order); empty when cost recording was off."""
+        n = C.c_uint64(0)
+        self._ck(self.lib.cuda_trace_download_strip_cycles(self.h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, np.uint32)
+        if n.value:
+            self._ck(self.lib.cuda_trace_download_strip_cycles(self.h, _p(out, _U32P), n.value, C.byref(n)))
+        return out
 
     def ray_march(self, origins, dirs):
         o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)

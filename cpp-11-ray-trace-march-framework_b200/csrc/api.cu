@@ -1307,4 +1307,22 @@ int cuda_trace_get_counters(cuda_trace_ctx *ctx, cuda_trace_counters *out)
     return 0;
 }
 
+int cuda_trace_download_strip_cycles(cuda_trace_ctx *ctx, uint32_t *cycles, uint64_t capacity, uint64_t *count)
+{
+    if (!ctx || !count || (capacity && !cycles))
+        return CUDA_TRACE_ERR_ARG;
+    int rc = cuda_trace_sync(ctx);
+    if (rc)
+        return rc;
+    DeviceState& d = ctx->dev[0];
+    *count = (d.order_valid && d.order_signature.size() > 10) ? d.order_signature[10] : 0;
+    const uint64_t n = std::min<uint64_t>(*count, capacity);
+    if (n)
+    {
+        CK(cudaSetDevice(d.ordinal));
+        CK(cudaMemcpy(cycles, d.d_strip_cycles, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
 } // extern "C"

@@ -202,6 +202,10 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
                     p.framebuffer[(size_t) py * p.width + px] = resolve_pixel(acc, spp_f, p.gamma != 0);
             }
         }
+        // this strip's cost, for the next frame's visiting order (schedule.cu).  Every lane stores the same word
+        // (one transaction): a lane-0 branch here would make the compiler guard the traversal's votes again
+        if (p.strip_cycles)
+            p.strip_cycles[fetch] = (uint32_t) min(__shfl_sync(kFull, clock64() - t_begin, 0), 0x7FFFFFFFll);
         // (compiled out of the BANDS == false instantiation: the warp barrier in here makes the compiler
         // guard every vote of the traversal with a divergence check, +3 instructions per triangle test)
         if (BANDS && p.band_done)

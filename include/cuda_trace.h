@@ -211,6 +211,11 @@ int cuda_trace_qmc_cranley_patterson(cuda_trace_ctx *ctx, const double *x, doubl
 int cuda_trace_set_counting(cuda_trace_ctx *ctx, int enable);
 int cuda_trace_get_counters(cuda_trace_ctx *ctx, cuda_trace_counters *out);
 
+/* Scheduler diagnostics: SM cycles each strip of the last frame took on device 0, in this shard's strip order
+ * (the input of the cost-ordered scheduling, csrc/schedule.cu).  *count = strips recorded (0 when the last frame
+ * ran without cost recording -- see RTM_COST_ORDER); at most `capacity` values are written. */
+int cuda_trace_download_strip_cycles(cuda_trace_ctx *ctx, uint32_t *cycles, uint64_t capacity, uint64_t *count);
+
 /* Page-locked host memory for the framebuffer passed to cuda_trace_tiles / read_framebuffer: the
  * device-to-host copy is then a single DMA at full PCIe rate.  Any other host memory works too
  * (the driver stages it), only slower.  Free with cuda_trace_host_free. */
