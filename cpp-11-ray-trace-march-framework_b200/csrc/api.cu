@@ -55,7 +55,7 @@ struct DeviceState
     Counters *d_counters = nullptr;
     void *d_l2_scratch = nullptr;
     // cost-ordered scheduling (schedule.cu): cycles per strip of the last frame -> order of the next
-    uint32_t *d_strip_cycles = nullptr, *d_fetch_order = nullptr, *d_order_scratch = nullptr;
+    uint32_t *d_strip_cycles = nullptr, *d_fetch_order = nullptr, *d_order_scratch = nullptr, *d_visit_total = nullptr, *d_visit_cycles = nullptr;
     unsigned long long *d_cost_sum = nullptr;
     uint32_t order_cap = 0;
     bool order_valid = false;
@@ -245,7 +245,7 @@ uint32_t *band_counters(cuda_trace_ctx *ctx)
 // Strips per row band for this frame layout (a strip that straddles a band boundary counts in
 // both, exactly as the kernel bumps both)
 void band_increments(const std::vector<uint4>& rects, uint32_t strip_w, uint32_t strip_h, uint32_t band_rows,
-                     uint32_t *inc)
+                     uint32_t parts, uint32_t *inc)
 {
     std::memset(inc, 0, sizeof(uint32_t) * kMaxBands);
     for (const uint4& r : rects)
@@ -254,9 +254,9 @@ void band_increments(const std::vector<uint4>& rects, uint32_t strip_w, uint32_t
         for (uint32_t y = r.y; y < r.w; y += strip_h)
         {
             const uint32_t b0 = y / band_rows, b1 = (std::min(y + strip_h, r.w) - 1) / band_rows;
-            inc[b0] += nx;
+            inc[b0] += nx * parts; // the counters count pieces of strips (strip_split_parts)
             if (b1 != b0)
-                inc[b1] += nx;
+                inc[b1] += nx * parts;
         }
     }
 }
@@ -393,6 +393,7 @@ void cuda_trace_destroy(cuda_trace_ctx *ctx)
         cudaFree(d.d_smp); cudaFree(d.d_tile_rects); cudaFree(d.d_tile_prefix); cudaFree(d.d_strip_counter);
         cudaFree(d.d_cancel); cudaFree(d.d_counters); cudaFree(d.d_l2_scratch);
         cudaFree(d.d_strip_cycles); cudaFree(d.d_fetch_order); cudaFree(d.d_cost_sum); cudaFree(d.d_order_scratch);
+        cudaFree(d.d_visit_total); cudaFree(d.d_visit_cycles);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
         if (d.stream) cudaStreamDestroy(d.stream);
@@ -646,6 +647,10 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
             strip_h = px >= 16 ? 4 : (px >= 4 ? 2 : 1);
         }
     }
+    uint32_t split_parts = strip_split_parts(strip_w, strip_h, f->spp);
+    if (const char *e = std::getenv("RTM_SPLIT_PARTS")) // tuning override (experiments only): 1 = never split
+        if (std::atoi(e) == 1 || (std::atoi(e) == 2 && split_parts >= 2))
+            split_parts = (uint32_t) std::atoi(e);
     std::vector<uint4> rects(n_tiles);
     std::vector<uint32_t> prefix(n_tiles + 1, 0);
     uint64_t total = 0;
@@ -711,7 +716,7 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
     {
         ctx->band_rows = std::max<uint32_t>(strip_h, (f->height + 15) / 16);
         ctx->n_bands = (f->height + ctx->band_rows - 1) / ctx->band_rows;
-        std::vector<uint32_t> bsig = { f->width, f->height, strip_w, strip_h, n_tiles, ctx->band_rows };
+        std::vector<uint32_t> bsig = { f->width, f->height, strip_w, strip_h, n_tiles, ctx->band_rows, split_parts };
         for (uint32_t k = 0; k < n_tiles; k++)
         {
             bsig.push_back(rects[k].x ^ (rects[k].z << 16));
@@ -719,7 +724,7 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
         }
         if (bsig != ctx->band_inc_sig)
         {
-            band_increments(rects, strip_w, strip_h, ctx->band_rows, ctx->band_inc);
+            band_increments(rects, strip_w, strip_h, ctx->band_rows, split_parts, ctx->band_inc);
             ctx->band_inc_sig = bsig;
         }
         for (uint32_t b = 0; b < ctx->n_bands; b++)
@@ -837,6 +842,8 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
         p.n_tiles = n_tiles;
         p.strip_w = strip_w;
         p.strip_h = strip_h;
+        p.split_parts = split_parts;
+        p.visit_total = nullptr;
         p.total_strips = (uint32_t) total;
         // strips are interleaved first over the processes (shard), then over this context's devices
         p.shard_world = ctx->shard_world * n_dev;
@@ -871,31 +878,36 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
                 sig.push_back(rects[k].y ^ (rects[k].w << 16));
             }
             p.fetch_order = nullptr;
-            p.strip_cycles = nullptr;
+            p.visit_cycles = nullptr;
             // worth its ~1 % instrumentation cost when the frame is sharded or small (the tail of
             // expensive strips is then a large part of the launch); RTM_COST_ORDER=0/1 forces it
-            const bool want_order = ctx->cost_order_forced >= 0 ? ctx->cost_order_forced != 0
-                                   : (p.shard_world > 1 || (uint64_t) f->width * f->height * f->spp < (64ull << 20));
+            const bool want_order = (ctx->cost_order_forced >= 0 ? ctx->cost_order_forced != 0
+                                    : (p.shard_world > 1 || (uint64_t) f->width * f->height * f->spp < (64ull << 20))) &&
+                                    shard_strips <= kVisitStripMask;
             if (want_order && shard_strips > 0)
             {
                 if (d.order_cap < shard_strips)
                 {
-                    cudaFree(d.d_strip_cycles); cudaFree(d.d_fetch_order); cudaFree(d.d_order_scratch);
-                    d.d_strip_cycles = d.d_fetch_order = d.d_order_scratch = nullptr;
+                    cudaFree(d.d_strip_cycles); cudaFree(d.d_fetch_order); cudaFree(d.d_order_scratch); cudaFree(d.d_visit_cycles);
+                    d.d_strip_cycles = d.d_fetch_order = d.d_order_scratch = d.d_visit_cycles = nullptr;
                     d.order_cap = 0;
                     d.order_valid = false;
                     CK(cudaMalloc(&d.d_strip_cycles, sizeof(uint32_t) * shard_strips));
-                    CK(cudaMalloc(&d.d_fetch_order, sizeof(uint32_t) * shard_strips));
+                    CK(cudaMalloc(&d.d_fetch_order, sizeof(uint32_t) * strip_order_capacity(shard_strips, 4)));
+                    CK(cudaMalloc(&d.d_visit_cycles, sizeof(uint32_t) * strip_order_capacity(shard_strips, 4)));
                     CK(cudaMalloc(&d.d_order_scratch, sizeof(uint32_t) * strip_order_scratch_words(shard_strips)));
                     if (!d.d_cost_sum)
                         CK(cudaMalloc(&d.d_cost_sum, sizeof(unsigned long long)));
+                    if (!d.d_visit_total)
+                        CK(cudaMalloc(&d.d_visit_total, sizeof(uint32_t)));
                     d.order_cap = shard_strips;
                 }
                 if (d.order_valid && sig == d.order_signature)
                     p.fetch_order = d.d_fetch_order;
+                p.visit_total = d.d_visit_total;
                 d.order_signature = sig;
-                p.strip_cycles = d.d_strip_cycles;
-                CK(cudaMemsetAsync(d.d_strip_cycles, 0, sizeof(uint32_t) * shard_strips, d.stream));
+                p.visit_cycles = d.d_visit_cycles;
+                CK(cudaMemsetAsync(d.d_visit_cycles, 0, sizeof(uint32_t) * strip_order_capacity(shard_strips, split_parts), d.stream));
             }
             else
                 d.order_valid = false;
@@ -912,12 +924,12 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
             ctx->launches++;
         }
         CK(cudaEventRecord(d.ev_end, d.stream));
-        if (p.strip_cycles && total)
+        if (p.visit_cycles && total)
         {
             // this frame's strip costs -> next frame's visiting order (off the timed kernel)
-            launch_build_strip_order(d.d_strip_cycles, (uint32_t) d.order_signature[10], d.d_cost_sum, d.d_order_scratch,
-                                     d.d_fetch_order, d.stream);
-            ctx->launches += 4;
+            launch_build_strip_order(d.d_visit_cycles, p.fetch_order != nullptr, d.d_strip_cycles, (uint32_t) d.order_signature[10],
+                                     split_parts, d.d_cost_sum, d.d_order_scratch, d.d_visit_total, d.d_fetch_order, d.stream);
+            ctx->launches += 5;
             d.order_valid = true;
         }
         CK(cudaGetLastError());

@@ -7,6 +7,9 @@
 // sharded one.  K1 records the cycles each strip took; after the frame this file turns them into
 // the NEXT frame's visiting order: expensive strips (> 2x the mean) first, everything else behind
 // them in image order (a stable partition, so L1 locality of neighbouring strips is kept).
+// An expensive strip is also SPLIT: it is visited as `parts` pieces of whole 32-ray rounds (whole
+// pixels), taken by different warps -- the costliest killeroo strip runs 1.6 ms as one piece, most of
+// an 8-way shard's 1.9 ms frame.  A visit entry = strip | (piece + 1) << 28 (0 on top = whole strip).
 // The order only affects scheduling, never results; a frame whose layout differs from the
 // previous one simply runs in image order.
 #include "trace_kernels.cuh"
@@ -16,6 +19,22 @@ namespace rtm
 
 namespace
 {
+
+// K1 records cycles per VISIT; a strip split into pieces was visited several times
+__global__ void visit_costs_to_strips_kernel(const uint32_t *__restrict__ visit_cycles, const uint32_t *__restrict__ order,
+                                             const uint32_t *__restrict__ visit_total, uint32_t n,
+                                             uint32_t *__restrict__ strip_cycles)
+{
+    const uint32_t visits = order ? *visit_total : n;
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < visits; v += gridDim.x * blockDim.x)
+    {
+        const uint32_t c = visit_cycles[v];
+        if (!order)
+            strip_cycles[v] = c;
+        else if (c)
+            atomicAdd(&strip_cycles[order[v] & kVisitStripMask], c);
+    }
+}
 
 __global__ void cost_sum_kernel(const uint32_t *__restrict__ cycles, uint32_t n, unsigned long long *__restrict__ sum)
 {
@@ -102,6 +121,7 @@ __global__ void __launch_bounds__(1024) order_scan_kernel(const uint32_t *__rest
 __global__ void __launch_bounds__(kOrderBlock) order_scatter_kernel(const uint32_t *__restrict__ cycles, uint32_t n,
                                                                     const unsigned long long *__restrict__ sum,
                                                                     const uint32_t *__restrict__ block_base, uint32_t nb,
+                                                                    uint32_t parts, uint32_t *__restrict__ visit_total,
                                                                     uint32_t *__restrict__ order)
 {
     __shared__ uint32_t s_warp[kOrderBlock / 32];
@@ -115,7 +135,17 @@ __global__ void __launch_bounds__(kOrderBlock) order_scatter_kernel(const uint32
     if (i < n)
     {
         const uint32_t heavy_rank = block_base[blockIdx.x] + before + __popc(ballot & ((1u << lane) - 1u));
-        order[heavy ? heavy_rank : block_base[nb] + (i - heavy_rank)] = i; // expensive first, both halves in image order
+        // expensive first (each as `parts` consecutive pieces), both halves in image order
+        const uint32_t n_heavy = block_base[nb];
+        if (!heavy)
+            order[n_heavy * parts + (i - heavy_rank)] = i;
+        else if (parts == 1)
+            order[heavy_rank] = i;
+        else
+            for (uint32_t k = 0; k < parts; k++)
+                order[heavy_rank * parts + k] = i | ((k + 1u) << 28);
+        if (i == 0)
+            *visit_total = n + n_heavy * (parts - 1u);
     }
 }
 
@@ -127,19 +157,31 @@ size_t strip_order_scratch_words(uint32_t n)
     return 2 * nb + 2;
 }
 
-// cycles[n] (written by K1) -> order[n]; sum and scratch are work buffers.  4 kernels + one memset.
-void launch_build_strip_order(const uint32_t *cycles, uint32_t n, unsigned long long *sum, uint32_t *scratch,
+// "expensive" = above twice the mean, so fewer than n / 2 strips are split
+size_t strip_order_capacity(uint32_t n, uint32_t parts)
+{
+    return (size_t) n + ((size_t) n / 2 + 1) * (parts - 1);
+}
+
+// cycles[n] (written by K1) -> order[*visit_total]; sum and scratch are work buffers.  5 kernels + memsets.
+void launch_build_strip_order(const uint32_t *visit_cycles, bool order_was_used, uint32_t *strip_cycles, uint32_t n,
+                              uint32_t parts, unsigned long long *sum, uint32_t *scratch, uint32_t *visit_total,
                               uint32_t *order, cudaStream_t stream)
 {
     if (n == 0)
         return;
+    if (order_was_used)
+        cudaMemsetAsync(strip_cycles, 0, sizeof(uint32_t) * n, stream);
+    visit_costs_to_strips_kernel<<<296, 512, 0, stream>>>(visit_cycles, order_was_used ? order : nullptr, visit_total, n,
+                                                          strip_cycles);
+    const uint32_t *cycles = strip_cycles;
     const uint32_t nb = (n + kOrderBlock - 1) / kOrderBlock;
     uint32_t *block_count = scratch, *block_base = scratch + nb;
     cudaMemsetAsync(sum, 0, sizeof(unsigned long long), stream);
     cost_sum_kernel<<<64, 256, 0, stream>>>(cycles, n, sum);
     order_count_kernel<<<nb, kOrderBlock, 0, stream>>>(cycles, n, sum, block_count);
     order_scan_kernel<<<1, 1024, 0, stream>>>(block_count, nb, block_base);
-    order_scatter_kernel<<<nb, kOrderBlock, 0, stream>>>(cycles, n, sum, block_base, nb, order);
+    order_scatter_kernel<<<nb, kOrderBlock, 0, stream>>>(cycles, n, sum, block_base, nb, parts, visit_total, order);
 }
 
 } // namespace rtm

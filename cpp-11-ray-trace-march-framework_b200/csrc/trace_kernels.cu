@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
     Counters cnt = { 0, 0, 0, 0 };
 
     const uint32_t slots = p.strip_w * p.strip_h;
-    uint32_t pend_band = 0, pend_count = 0; // finished strips not yet published (see publish_band)
+    uint32_t pend_band = 0, pend_count = 0; // finished pieces not yet published (see the band publication below)
+    const uint32_t n_visits = p.fetch_order ? __ldg(p.visit_total) : p.shard_strips;
+    const uint32_t part_slots = slots / p.split_parts;
     for (;;)
     {
         // dynamic strip scheduler: one atomic per strip per warp
@@ -102,16 +104,22 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         // a VOTE result is warp-uniform by construction, which lets the compiler keep the traversal
         // below free of divergence checks around its own votes
         const bool cancelled = __any_sync(kFull, cancel_seen);
-        if (__any_sync(kFull, visit >= p.shard_strips) || (cancelled && !(BANDS && p.band_done)))
+        if (__any_sync(kFull, visit >= n_visits) || (cancelled && !(BANDS && p.band_done)))
             break;
         // `fetch` = index of the strip within this shard, taken through the cost order of the
         // previous frame when there is one (schedule.cu)
         // (broadcast through a shuffle: a loaded value is not provably warp-uniform, and everything
         // derived from it -- strip, rectangle, loop bounds -- would make the compiler guard the
         // traversal's votes with divergence checks: +3 instructions per triangle test)
-        const uint32_t fetch = __shfl_sync(kFull, p.fetch_order ? __ldg(&p.fetch_order[visit]) : visit, 0);
-        const long long t_begin = p.strip_cycles ? clock64() : 0;
-        const uint32_t slot_begin = 0, slot_end = slots;
+        const uint32_t entry = __shfl_sync(kFull, p.fetch_order ? __ldg(&p.fetch_order[visit]) : visit, 0);
+        // an entry of the cost order names a whole strip or, for a strip that was expensive in the previous
+        // frame, one of its split_parts pieces (whole rounds of whole pixels -- results do not depend on it)
+        const uint32_t piece = p.fetch_order ? entry >> 28 : 0u;
+        const uint32_t fetch = p.fetch_order ? entry & kVisitStripMask : entry;
+        const long long t_begin = p.visit_cycles ? clock64() : 0;
+        const uint32_t slot_begin = piece ? (piece - 1u) * part_slots : 0u;
+        const uint32_t slot_end = piece ? slot_begin + part_slots : slots;
+        const uint32_t units = piece ? 1u : p.split_parts; // band counters count pieces
         // the n-th strip of this shard: strips are dealt out in chunks of p.shard_chunk consecutive
         // ids (neighbouring strips stay on one GPU / in one CTA: their rays share triangle records
         // in L1), round-robin over the shards, the owner rotating from round to round so that
@@ -151,12 +159,14 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
             // walk nearly the same cells.
             const uint32_t ppr = 32u / p.spp;
             const uint32_t pl = lane / p.spp, s = lane - pl * p.spp;
-            for (uint32_t pbase = slot_begin; pbase < slot_end; pbase += ppr)
+            // (uniform loop bounds + a vote to skip the rounds outside this piece: bounds derived from the
+            // visit entry would count as possibly divergent and bring the vote guards back)
+            for (uint32_t pbase = 0; pbase < slots; pbase += ppr)
             {
                 const uint32_t slot = pbase + pl;
                 const uint32_t ox = (slot & 1u) | ((slot >> 1) & 2u) | ((slot >> 2) & 4u);
                 const uint32_t oy = ((slot >> 1) & 1u) | ((slot >> 2) & 2u);
-                const bool active = pl < ppr && slot < slot_end && ox < bw && oy < bh;
+                const bool active = pl < ppr && slot >= slot_begin && slot < slot_end && ox < bw && oy < bh;
                 if (!__any_sync(kFull, active))
                     continue;
                 const uint32_t px = bx0 + ox, py = by0 + oy;
@@ -179,11 +189,12 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         {
             // one pixel at a time, 32 samples per round.  (No `continue` in this loop: with one the
             // compiler treats the whole strip loop as possibly divergent and guards every vote.)
-            for (uint32_t slot = slot_begin; slot < slot_end; slot++)
+            for (uint32_t slot = 0; slot < slots; slot++)
             {
                 const uint32_t ox = (slot & 1u) | ((slot >> 1) & 2u) | ((slot >> 2) & 4u);
                 const uint32_t oy = ((slot >> 1) & 1u) | ((slot >> 2) & 2u);
-                const bool inside = ox < bw && oy < bh; // clipped strips: the pixel lies outside the tile
+                // clipped strips: the pixel lies outside the tile; split strips: outside this piece
+                const bool inside = slot >= slot_begin && slot < slot_end && ox < bw && oy < bh;
                 const uint32_t px = bx0 + ox, py = by0 + oy;
                 float3 acc = make_float3(0.0f, 0.0f, 0.0f);
                 for (uint32_t sb = 0; sb < p.spp; sb += 32)
@@ -202,10 +213,11 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
                     p.framebuffer[(size_t) py * p.width + px] = resolve_pixel(acc, spp_f, p.gamma != 0);
             }
         }
-        // this strip's cost, for the next frame's visiting order (schedule.cu).  Every lane stores the same word
-        // (one transaction): a lane-0 branch here would make the compiler guard the traversal's votes again
-        if (p.strip_cycles)
-            p.strip_cycles[fetch] = (uint32_t) min(__shfl_sync(kFull, clock64() - t_begin, 0), 0x7FFFFFFFll);
+        // this visit's cost; schedule.cu sums the pieces per strip for the next frame's visiting order.  Every lane
+        // stores the same word (one transaction): a lane-0 branch, or an atomic in inline PTX, would make the
+        // compiler guard the traversal's votes again
+        if (p.visit_cycles)
+            p.visit_cycles[visit] = (uint32_t) min(__shfl_sync(kFull, clock64() - t_begin, 0), 0x0FFFFFFFll);
         // (compiled out of the BANDS == false instantiation: the warp barrier in here makes the compiler
         // guard every vote of the traversal with a divergence check, +3 instructions per triangle test)
         if (BANDS && p.band_done)
@@ -217,7 +229,7 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
             // The host's copy stream waits on these counters and ships each row band to the host
             // while later bands are still being traced.
             const uint32_t b0 = by0 / p.band_rows, b1 = (by0 + bh - 1) / p.band_rows;
-            const bool flush = pend_count && (pend_band != b0 || pend_count >= 8u);
+            const bool flush = pend_count && (pend_band != b0 || pend_count >= 8u * p.split_parts);
             __syncwarp(); // unconditional, at the top level of the strip loop (a barrier under a
                           // data-dependent branch would make the compiler guard every vote in the loop)
             if (lane == 0)
@@ -225,12 +237,12 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
                 if (flush)
                     release_add(p, pend_band, pend_count);
                 if (b1 != b0)
-                    release_add(p, b1, 1u); // a strip straddling two bands counts in both
+                    release_add(p, b1, units); // a strip straddling two bands counts in both
             }
             if (flush)
                 pend_count = 0;
             pend_band = b0;
-            pend_count++;
+            pend_count += units;
         }
     }
     if (BANDS && p.band_done)

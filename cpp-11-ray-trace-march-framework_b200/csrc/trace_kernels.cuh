@@ -20,6 +20,14 @@ inline void strip_size_for_spp(uint32_t spp, uint64_t frame_rays, uint32_t& w, u
     w = pixels >= 32 ? 8 : (pixels >= 8 ? 4 : 2);
     h = pixels >= 16 ? 4 : (pixels >= 4 ? 2 : 1);
 }
+// A strip the previous frame found expensive is handed out in `parts` pieces (whole rounds of 32 rays, whole
+// pixels) so that no single warp holds the end of the frame: 4, 2 or 1 pieces (schedule.cu)
+inline uint32_t strip_split_parts(uint32_t strip_w, uint32_t strip_h, uint32_t spp)
+{
+    const uint32_t slots = strip_w * strip_h, ppr = spp <= 32 ? 32u / spp : 1u; // pixels per round
+    return slots % (4 * ppr) == 0 ? 4u : (slots % (2 * ppr) == 0 ? 2u : 1u);
+}
+constexpr uint32_t kVisitStripMask = 0x0FFFFFFFu; // visit entry = strip in shard | (part + 1) << 28, 0 in the top bits = whole strip
 constexpr int kMaxBands = 32;          // row bands of the overlapped framebuffer read-back (api.cu)
 constexpr int kTraceMaxThreads = 1024; // launch bound (caps the kernel at 64 registers); actual CTA size is chosen per launch
 
@@ -48,8 +56,10 @@ struct TraceParams
     uint32_t total_strips;
     uint32_t shard_rank, shard_world;  // this launch renders the strips of shard `rank` out of `world`
     uint32_t shard_chunk;              // consecutive strips per deal (see trace_tiles_kernel)
-    const uint32_t *fetch_order;       // cost-ordered visiting order of this shard's strips (schedule.cu) or null
-    uint32_t *strip_cycles;            // out: cycles spent per strip of this shard (feeds the next frame's order) or null
+    const uint32_t *fetch_order;       // cost-ordered visit list of this shard (schedule.cu) or null = strips in image order
+    const uint32_t *visit_total;       // device word: entries in fetch_order
+    uint32_t split_parts;              // pieces an expensive strip is visited in (strip_split_parts); band counters count pieces
+    uint32_t *visit_cycles;            // out: cycles spent per visit (feeds the next frame's order, schedule.cu) or null
     uint32_t *strip_counter;           // dynamic strip scheduler (zeroed before launch)
     const uint32_t *cancel;            // non-zero => stop fetching strips
     uint32_t *framebuffer;             // width * height, row 0 = y 0 (may be a peer / IPC pointer)
@@ -82,10 +92,15 @@ void launch_ray_march(const float *vtx, const uint32_t *tri, uint32_t num_tri, u
                       const float *dirs, uint32_t *hit, float *t, cudaStream_t stream);
 void launch_brute_force(const float *vtx, const uint32_t *tri, uint32_t num_tri, const RayBatchParams& p, cudaStream_t stream);
 
-// cost-ordered scheduling (schedule.cu): 4 kernels; scratch = 2 * ceil(n / 1024) + 2 words
-void launch_build_strip_order(const uint32_t *cycles, uint32_t n, unsigned long long *sum, uint32_t *scratch,
+// cost-ordered scheduling (schedule.cu): 5 kernels; scratch = 2 * ceil(n / 1024) + 2 words; order holds up to
+// strip_order_capacity(n, parts) visit entries, *visit_total how many were written.  visit_cycles = what K1
+// recorded for this frame's visits (made through `order` when order_was_used, else strip by strip);
+// strip_cycles[n] receives the per-strip sums.
+void launch_build_strip_order(const uint32_t *visit_cycles, bool order_was_used, uint32_t *strip_cycles, uint32_t n,
+                              uint32_t parts, unsigned long long *sum, uint32_t *scratch, uint32_t *visit_total,
                               uint32_t *order, cudaStream_t stream);
 size_t strip_order_scratch_words(uint32_t n);
+size_t strip_order_capacity(uint32_t n, uint32_t parts);
 
 // scene packing (pack.cu)
 void launch_pack_cell_tris(const float *vtx, const uint32_t *tri, const uint32_t *tri_index, uint64_t num_refs,

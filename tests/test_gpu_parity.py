@@ -274,3 +274,45 @@ def test_errors(cuda_trace, scene_data):
         ct.close()
     with pytest.raises(capi.CudaTraceError):
         capi.CudaTrace(devices=[99])
+
+
+def test_cost_ordered_split_frames_match_image_order(ref, scene_data):
+    """Scheduling must never change results.  Frames 2.. of one layout run through the cost order of the previous
+    frame, with its expensive strips split into pieces (csrc/schedule.cu); the camera moves between frames so a
+    skipped piece cannot hide behind a stale pixel.  1080p / 16 spp: 128-ray strips, 4 pieces, order on by default;
+    both the plain read-back and the overlapped per-band one (whose counters count pieces) are used."""
+    capi, scenes = pkg("capi"), pkg("scenes")
+    sd = scene_data("killeroo")
+    w, h, spp = 1920, 1080, 16
+    fov_xs, aspect = ref.api.camera_constants(sd.fov, w, h)
+    cams = []
+    for eye_x in (-1.6, -1.5, -1.4):
+        cams.append(ref.api.look_at((eye_x, 1.2, -1.0), (0.0, 0.0, -0.1)))
+    fresh = capi.CudaTrace(1)
+    fresh.upload_scene(sd.vtx, sd.tri, 64)
+    want = []
+    for cam in cams:  # every frame in image order: a new layout (different tiles) in between invalidates the order
+        fresh.trace_tiles(fresh.make_frame(64, 64, 1, cam, fov_xs, aspect))
+        want.append(fresh.trace_tiles(fresh.make_frame(w, h, spp, cam, fov_xs, aspect)).copy())
+    m, fov, _ = scenes.build(ref.api, "killeroo")
+    _, ref_img = ref.renderer(m, fov, cams[0]).render(w, h, spp)
+    assert np.array_equal(want[0], ref_img)
+    fresh.close()
+
+    ct = capi.CudaTrace(1)
+    ct.upload_scene(sd.vtx, sd.tri, 64)
+    pinned = capi.PinnedImage(w, h)
+    for k, cam in enumerate(cams):
+        f = ct.make_frame(w, h, spp, cam, fov_xs, aspect)
+        ct.trace_tiles_async(f)
+        got = ct.read_framebuffer(np.zeros((h, w), np.uint32))
+        assert np.array_equal(got, want[k]), "frame %d (plain read-back)" % k
+        cyc = ct.strip_cycles()
+        assert len(cyc) == (w // 4) * (h // 2) and int((cyc == 0).sum()) == 0  # every strip was visited and timed
+    for k, cam in enumerate(cams):
+        pinned.array[:] = 0
+        ct.trace_tiles(ct.make_frame(w, h, spp, cam, fov_xs, aspect), out=pinned.array)
+        assert np.array_equal(pinned.array, want[k]), "frame %d (overlapped read-back)" % k
+    heavy = ct.strip_cycles()
+    assert heavy.max() > 4 * heavy.mean()  # the premise: strip costs are very uneven
+    ct.close()
