@@ -216,7 +216,7 @@ def run_ours(args, wl, rank, world, local_rank, dist):
     ct.set_shard(rank, world)
     fov_xs, aspect = host.camera_constants(fov, w, h)
     frame = ct.make_frame(w, h, spp, cam, fov_xs, aspect)
-    rects = capi.full_frame_tiles(w, h)
+    rects = capi.CudaTrace.make_tiles(capi.full_frame_tiles(w, h))  # converted once: the layout repeats every frame
 
     # rank 0 owns the framebuffer; the others map it (CUDA IPC) and store into it over NVLink
     multirank = pkg("multirank")
@@ -262,6 +262,8 @@ def run_ours(args, wl, rank, world, local_rank, dist):
         ct.set_shard_signals(True)
         barrier()
     e2e_s = 0.0
+    e2e_kernel_ms = np.zeros(args.steps, np.float64)   # the trace kernel inside the end-to-end region (max over ranks)
+    e2e_marks = np.zeros(7, np.float64)                # rank 0: submitted / traced / copied / returned, ms since call entry
     for i in range(args.steps):
         ct.flush_l2()
         ct.sync()
@@ -277,7 +279,18 @@ def run_ours(args, wl, rank, world, local_rank, dist):
             ct.sync()
         barrier()
         e2e_s += time.perf_counter() - t0
+        e2e_kernel_ms[i] = ct.last_kernel_ms()
+        if rank == 0:
+            e2e_marks += np.array(ct.last_call_timing()) / args.steps
     e2e_s = float(group.allreduce_max([e2e_s])[0])
+    mine = np.zeros(world, np.float64)
+    mine[rank] = e2e_kernel_ms.mean()
+    e2e_kernel_by_rank = group.allreduce_sum(mine)     # diagnostics: each rank's kernel inside the end-to-end region
+    e2e_kernel_ms = group.allreduce_max(e2e_kernel_ms)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        barrier()
+    barrier_ms = float(group.allreduce_max([(time.perf_counter() - t0) / 20 * 1e3])[0])
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- work counters of this frame (untimed, instrumented kernel) for the roofline figures
@@ -308,6 +321,10 @@ def run_ours(args, wl, rank, world, local_rank, dist):
                    "scene_upload_and_grid_build_s": upload_s},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": METRIC, "ms_per_step": 1e3 * e2e_s / args.steps,
+                "kernel_ms_per_step": float(e2e_kernel_ms.mean()),
+                "kernel_ms_by_rank": [round(float(x), 4) for x in e2e_kernel_by_rank], "barrier_ms": barrier_ms,
+                "rank0_call_ms": {"prepared": e2e_marks[4], "launching": e2e_marks[5], "launched": e2e_marks[6],
+                                  "submitted": e2e_marks[0], "traced": e2e_marks[1], "copied": e2e_marks[2], "returned": e2e_marks[3]},
                 "h2d_bytes_per_step": 108 * 16 + 109 * 4, "d2h_bytes_per_step": w * h * 4},
         "gpu_launches": int(launches),
         "step_ms": [round(float(x), 4) for x in step_ms],

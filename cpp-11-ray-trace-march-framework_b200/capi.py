@@ -65,6 +65,7 @@ SYMBOLS = {
     "cuda_trace_intersect_rays": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, C.c_uint32, _U32P, _F32P,
                                             _F32P, _F32P]),
     "cuda_trace_intersect_rays_brute_force": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P, _F32P, _F32P]),
+    "cuda_trace_last_call_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "cuda_trace_download_strip_cycles": (C.c_int, [C.c_void_p, _U32P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "cuda_trace_ray_march": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P]),
     "cuda_trace_sample_table": (C.c_int, [C.c_void_p, C.c_uint32, _F32P]),
@@ -226,28 +227,32 @@ class CudaTrace:
 
     @staticmethod
     def make_tiles(rects):
+        """list of (x0, y0, x1, y1) -> (TileRect array, count); a result of make_tiles passes through, so a
+        caller rendering the same layout every frame converts it once."""
+        if isinstance(rects, tuple) and len(rects) == 2 and isinstance(rects[0], C.Array):
+            return rects
         arr = (TileRect * max(len(rects), 1))()
         for i, r in enumerate(rects):
             arr[i].x0, arr[i].y0, arr[i].x1, arr[i].y1 = [int(v) for v in r]
-        return arr
+        return arr, len(rects)
 
     def trace_tiles(self, frame, rects=None, out=None, want_image=True):
         """Render ``rects`` (default: the reference's 12x9 layout of the whole frame) and return
         the host image [H, W] uint32 (row 0 = y 0)."""
         if rects is None:
             rects = full_frame_tiles(frame.width, frame.height)
-        tiles = self.make_tiles(rects)
+        tiles, n_tiles = self.make_tiles(rects)
         if want_image and out is None:
             out = np.zeros((frame.height, frame.width), np.uint32)
-        self._ck(self.lib.cuda_trace_tiles(self.h, C.byref(frame), tiles, len(rects),
+        self._ck(self.lib.cuda_trace_tiles(self.h, C.byref(frame), tiles, n_tiles,
                                            _p(out, _U32P) if want_image else None))
         return out
 
     def trace_tiles_async(self, frame, rects=None):
         if rects is None:
             rects = full_frame_tiles(frame.width, frame.height)
-        tiles = self.make_tiles(rects)
-        self._ck(self.lib.cuda_trace_tiles_async(self.h, C.byref(frame), tiles, len(rects)))
+        tiles, n_tiles = self.make_tiles(rects)
+        self._ck(self.lib.cuda_trace_tiles_async(self.h, C.byref(frame), tiles, n_tiles))
 
     def sync(self):
         self._ck(self.lib.cuda_trace_sync(self.h))
@@ -292,6 +297,13 @@ class CudaTrace:
         self._ck(self.lib.cuda_trace_intersect_rays_brute_force(self.h, n, _p(o, _F32P), _p(d, _F32P), _p(tri, _U32P),
                                                                 _p(t, _F32P), _p(u, _F32P), _p(v, _F32P)))
         return tri, t, u, v
+
+    def last_call_timing(self):
+        """ms since the entry of the last trace_tiles call: submitted, traced, copied, returned, prepared,
+        launching, launched."""
+        ms = (C.c_double * 7)()
+        self._ck(self.lib.cuda_trace_last_call_timing(self.h, ms))
+        return [float(x) for x in ms]
 
     def strip_cycles(self):
         """SM cycles per strip of the last frame (this shard's order); empty when cost recording was off."""

@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstdint>
+#include <array>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -34,6 +36,11 @@ struct DeviceState
     cudaStream_t stream = nullptr;
     cudaStream_t side_stream = nullptr; // cancel flag writes while the main stream is busy
     cudaStream_t copy_stream = nullptr; // overlapped framebuffer read-back (device 0 only)
+    // the next frame's visiting order is built behind the trace kernel on its own stream, so that waiting for the
+    // frame (cuda_trace_sync) does not wait for it; the next frame's launch does (ev_order)
+    cudaStream_t order_stream = nullptr;
+    cudaEvent_t ev_traced = nullptr, ev_order = nullptr;
+    bool order_pending = false;
     cudaEvent_t ev_copy = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 
@@ -51,7 +58,11 @@ struct DeviceState
     uint32_t *d_tile_prefix = nullptr;
     uint32_t tile_cap = 0;
     uint32_t *d_strip_counter = nullptr;
-    uint32_t *d_cancel = nullptr;
+    uint32_t *d_cancel = nullptr;          // = d_strip_counter + 1 (zeroed together, one memset per frame)
+    uint32_t *h_cancel_seen = nullptr;     // page-locked: the cancel flag as the frame's kernel left it
+    std::vector<uint32_t> layout_sig;      // tile list the device copies d_tile_rects / d_tile_prefix hold
+    std::vector<long long> occupancy_key;  // launch configuration `blocks_per_sm` was queried for
+    int blocks_per_sm = 0;
     Counters *d_counters = nullptr;
     void *d_l2_scratch = nullptr;
     // cost-ordered scheduling (schedule.cu): cycles per strip of the last frame -> order of the next
@@ -95,6 +106,7 @@ struct cuda_trace_ctx
     uint32_t band_expected[kMaxBands] = {};
     std::vector<uint32_t> band_inc_sig;
     uint32_t band_inc[kMaxBands] = {};
+    std::vector<std::array<uint32_t, kMaxBands>> band_share; // per participating GPU: its pieces of strips per band
     bool copy_pending = false;
     bool overlap_d2h = true;      // RTM_OVERLAP_D2H=0 disables
     bool shard_signals = false;   // cuda_trace_set_shard_signals: other ranks bump the counters too
@@ -110,6 +122,11 @@ struct cuda_trace_ctx
     std::vector<cuda_trace_tile_rect> tiles;
     bool frame_valid = false;
     float last_kernel_ms = 0.0f;
+    // host-clock marks of the last cuda_trace_tiles call, ms since its entry (cuda_trace_last_call_timing)
+    std::chrono::steady_clock::time_point t_enter;
+    double t_submitted_ms = 0.0, t_traced_ms = 0.0, t_copied_ms = 0.0, t_return_ms = 0.0;
+    double t_prepared_ms = 0.0, t_launching_ms = 0.0, t_launched_ms = 0.0; // submission in detail: host set-up done, first device's kernel about to be / has been launched
+    bool marks_armed = false;
     uint32_t *pinned_cancel_src = nullptr;
 
 };
@@ -244,20 +261,45 @@ uint32_t *band_counters(cuda_trace_ctx *ctx)
 
 // Strips per row band for this frame layout (a strip that straddles a band boundary counts in
 // both, exactly as the kernel bumps both)
-void band_increments(const std::vector<uint4>& rects, uint32_t strip_w, uint32_t strip_h, uint32_t band_rows,
-                     uint32_t parts, uint32_t *inc)
+double ms_since(std::chrono::steady_clock::time_point t0)
 {
-    std::memset(inc, 0, sizeof(uint32_t) * kMaxBands);
-    for (const uint4& r : rects)
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// Pieces of strips per row band for every participating GPU (`world` of them; strips dealt in chunks of
+// `chunk`, owner rotating from round to round -- the same arithmetic as in trace_tiles_kernel), and how many GPUs
+// have a share in each band.  A strip that straddles a band boundary counts in both, exactly as the kernel
+// bumps both.
+void band_shares(const std::vector<uint4>& rects, const std::vector<uint32_t>& prefix, uint32_t strip_w, uint32_t strip_h,
+                 uint32_t band_rows, uint32_t parts, uint32_t chunk, uint32_t world,
+                 std::vector<std::array<uint32_t, kMaxBands>>& share, uint32_t *gpus_in_band)
+{
+    share.assign(world, std::array<uint32_t, kMaxBands>());
+    for (size_t k = 0; k < rects.size(); k++)
     {
+        const uint4& r = rects[k];
         const uint32_t nx = (r.z - r.x + strip_w - 1) / strip_w;
-        for (uint32_t y = r.y; y < r.w; y += strip_h)
+        uint64_t row_first = prefix[k];
+        for (uint32_t y = r.y; y < r.w; y += strip_h, row_first += nx)
         {
             const uint32_t b0 = y / band_rows, b1 = (std::min(y + strip_h, r.w) - 1) / band_rows;
-            inc[b0] += nx * parts; // the counters count pieces of strips (strip_split_parts)
-            if (b1 != b0)
-                inc[b1] += nx * parts;
+            for (uint64_t s = row_first; s < row_first + nx;)
+            {
+                const uint64_t c = s / chunk, seg_end = std::min<uint64_t>(row_first + nx, (c + 1) * chunk);
+                const uint32_t owner = (uint32_t) ((c % world + c / world) % world);
+                const uint32_t n = (uint32_t) (seg_end - s) * parts;
+                share[owner][b0] += n;
+                if (b1 != b0)
+                    share[owner][b1] += n;
+                s = seg_end;
+            }
         }
+    }
+    for (int b = 0; b < kMaxBands; b++)
+    {
+        gpus_in_band[b] = 0;
+        for (uint32_t q = 0; q < world; q++)
+            gpus_in_band[b] += share[q][b] ? 1u : 0u;
     }
 }
 
@@ -314,14 +356,19 @@ int cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **
         if ((e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&d.side_stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&d.order_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.ev_traced, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.ev_order, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&d.ev_copy, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreate(&d.ev_begin)) != cudaSuccess || (e = cudaEventCreate(&d.ev_end)) != cudaSuccess ||
-            (e = cudaMalloc(&d.d_strip_counter, sizeof(uint32_t))) != cudaSuccess ||
-            (e = cudaMalloc(&d.d_cancel, sizeof(uint32_t))) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_strip_counter, (32 + kMaxBands) * sizeof(uint32_t))) != cudaSuccess || // {strip counter, cancel flag, pad to 128 B, band piece counts}
+            (e = cudaHostAlloc(&d.h_cancel_seen, sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess ||
             (e = cudaMalloc(&d.d_counters, sizeof(Counters))) != cudaSuccess ||
-            (e = cudaMemset(d.d_cancel, 0, sizeof(uint32_t))) != cudaSuccess ||
+            (e = cudaMemset(d.d_strip_counter, 0, (32 + kMaxBands) * sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMemset(d.d_counters, 0, sizeof(Counters))) != cudaSuccess)
             return bail(std::string("device set-up: ") + cudaGetErrorString(e), CUDA_TRACE_ERR_CUDA);
+        d.d_cancel = d.d_strip_counter + 1;
+        *d.h_cancel_seen = 0;
         if (i > 0)
         {
             // strips rendered on device i are stored straight into device 0's framebuffer
@@ -377,6 +424,7 @@ void cuda_trace_destroy(cuda_trace_ctx *ctx)
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
         if (d.copy_stream && !ctx->shard_signals) cudaStreamSynchronize(d.copy_stream);
+        if (d.order_stream) cudaStreamSynchronize(d.order_stream);
     }
     if (!ctx->dev.empty())
     {
@@ -391,7 +439,7 @@ void cuda_trace_destroy(cuda_trace_ctx *ctx)
     {
         free_scene(d);
         cudaFree(d.d_smp); cudaFree(d.d_tile_rects); cudaFree(d.d_tile_prefix); cudaFree(d.d_strip_counter);
-        cudaFree(d.d_cancel); cudaFree(d.d_counters); cudaFree(d.d_l2_scratch);
+        cudaFreeHost(d.h_cancel_seen); cudaFree(d.d_counters); cudaFree(d.d_l2_scratch);
         cudaFree(d.d_strip_cycles); cudaFree(d.d_fetch_order); cudaFree(d.d_cost_sum); cudaFree(d.d_order_scratch);
         cudaFree(d.d_visit_total); cudaFree(d.d_visit_cycles);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
@@ -399,6 +447,9 @@ void cuda_trace_destroy(cuda_trace_ctx *ctx)
         if (d.stream) cudaStreamDestroy(d.stream);
         if (d.side_stream) cudaStreamDestroy(d.side_stream);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+        if (d.order_stream) cudaStreamDestroy(d.order_stream);
+        if (d.ev_traced) cudaEventDestroy(d.ev_traced);
+        if (d.ev_order) cudaEventDestroy(d.ev_order);
         if (d.ev_copy) cudaEventDestroy(d.ev_copy);
     }
     if (ctx->pinned_cancel_src)
@@ -666,6 +717,12 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
             return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: too many strips");
     }
     prefix[n_tiles] = (uint32_t) total;
+    std::vector<uint32_t> layout_sig = { n_tiles, strip_w, strip_h };
+    for (uint32_t i = 0; i < n_tiles; i++)
+    {
+        layout_sig.push_back(rects[i].x); layout_sig.push_back(rects[i].y);
+        layout_sig.push_back(rects[i].z); layout_sig.push_back(rects[i].w);
+    }
 
     if ((rc = ensure_framebuffer(ctx, f->width, f->height)))
         return rc;
@@ -714,9 +771,18 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
     const bool use_bands = ctx->shard_signals || can_overlap || std::getenv("RTM_FORCE_BANDS") != nullptr;
     if (use_bands)
     {
-        ctx->band_rows = std::max<uint32_t>(strip_h, (f->height + 15) / 16);
+        // ~1 MB per band (a DMA that size runs at full PCIe rate; the last band's copy is the exposed tail), at
+        // most kMaxBands; a small frame is one band -- one wait and one copy instead of dozens of driver calls
+        const uint64_t frame_bytes = (uint64_t) f->width * f->height * sizeof(uint32_t);
+        const uint32_t want_bands = (uint32_t) std::min<uint64_t>(kMaxBands, std::max<uint64_t>(1, frame_bytes >> 20));
+        ctx->band_rows = std::max<uint32_t>(strip_h, (f->height + want_bands - 1) / want_bands);
         ctx->n_bands = (f->height + ctx->band_rows - 1) / ctx->band_rows;
-        std::vector<uint32_t> bsig = { f->width, f->height, strip_w, strip_h, n_tiles, ctx->band_rows, split_parts };
+        const uint32_t participants = ctx->shard_world * (uint32_t) ctx->dev.size();
+        // one GPU storing into its own framebuffer counts pieces straight into the band counters (a release at
+        // GPU scope is cheap); several GPUs count locally first and bump the shared counter once per band
+        const uint32_t two_level = (participants > 1 || ctx->fb_imported) ? 1u : 0u;
+        std::vector<uint32_t> bsig = { f->width, f->height, strip_w, strip_h, n_tiles, ctx->band_rows, split_parts,
+                                       participants, ctx->shard_chunk, two_level };
         for (uint32_t k = 0; k < n_tiles; k++)
         {
             bsig.push_back(rects[k].x ^ (rects[k].z << 16));
@@ -724,7 +790,11 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
         }
         if (bsig != ctx->band_inc_sig)
         {
-            band_increments(rects, strip_w, strip_h, ctx->band_rows, split_parts, ctx->band_inc);
+            band_shares(rects, prefix, strip_w, strip_h, ctx->band_rows, split_parts, ctx->shard_chunk, participants,
+                        ctx->band_share, ctx->band_inc);
+            if (!two_level)
+                for (int b = 0; b < kMaxBands; b++)
+                    ctx->band_inc[b] = ctx->band_share[0][b];
             ctx->band_inc_sig = bsig;
         }
         for (uint32_t b = 0; b < ctx->n_bands; b++)
@@ -732,6 +802,7 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
     }
 
     const uint32_t n_dev = (uint32_t) ctx->dev.size();
+    ctx->t_prepared_ms = ms_since(ctx->t_enter);
     for (uint32_t i = 0; i < n_dev; i++)
     {
         DeviceState& d = ctx->dev[i];
@@ -755,20 +826,31 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
             cudaFree(d.d_tile_rects); cudaFree(d.d_tile_prefix);
             d.d_tile_rects = nullptr; d.d_tile_prefix = nullptr;
             d.tile_cap = std::max<uint32_t>(n_tiles + 1, 128);
+            d.layout_sig.clear();
             CK(cudaMalloc(&d.d_tile_rects, sizeof(uint4) * d.tile_cap));
             CK(cudaMalloc(&d.d_tile_prefix, sizeof(uint32_t) * d.tile_cap));
         }
-        if (n_tiles)
-            CK(cudaMemcpyAsync(d.d_tile_rects, rects.data(), sizeof(uint4) * n_tiles, cudaMemcpyHostToDevice, d.stream));
-        CK(cudaMemcpyAsync(d.d_tile_prefix, prefix.data(), sizeof(uint32_t) * (n_tiles + 1), cudaMemcpyHostToDevice,
-                           d.stream));
-        CK(cudaMemsetAsync(d.d_strip_counter, 0, sizeof(uint32_t), d.stream));
-        CK(cudaMemsetAsync(d.d_cancel, 0, sizeof(uint32_t), d.stream));
+        // the tile list usually repeats from frame to frame: upload it only when it changed
+        const bool new_layout = d.layout_sig != layout_sig;
+        if (new_layout)
+        {
+            d.layout_sig.clear();
+            if (n_tiles)
+                CK(cudaMemcpyAsync(d.d_tile_rects, rects.data(), sizeof(uint4) * n_tiles, cudaMemcpyHostToDevice, d.stream));
+            CK(cudaMemcpyAsync(d.d_tile_prefix, prefix.data(), sizeof(uint32_t) * (n_tiles + 1), cudaMemcpyHostToDevice,
+                               d.stream));
+        }
+        // strip counter + cancel flag + this GPU's per-band piece counts
+        CK(cudaMemsetAsync(d.d_strip_counter, 0, (32 + kMaxBands) * sizeof(uint32_t), d.stream));
         if (ctx->counting)
             CK(cudaMemsetAsync(d.d_counters, 0, sizeof(Counters), d.stream));
-        // rects / prefix are pageable host vectors: the async copies above have consumed them
-        // only once the stream reaches them, so wait before they go out of scope
-        CK(cudaStreamSynchronize(d.stream));
+        if (new_layout)
+        {
+            // rects / prefix are pageable host vectors: the async copies above have consumed them
+            // only once the stream reaches them, so wait before they go out of scope
+            CK(cudaStreamSynchronize(d.stream));
+            d.layout_sig = layout_sig;
+        }
 
         TraceParams p;
         p.grid = grid_dev(ctx, d);
@@ -854,6 +936,10 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
         p.framebuffer = ctx->d_fb;
         p.band_done = use_bands ? band_counters(ctx) : nullptr;
         p.band_rows = ctx->band_rows;
+        p.band_local = (ctx->shard_world * n_dev > 1 || ctx->fb_imported) ? d.d_strip_counter + 32 : nullptr; // own cache line
+        std::memset(p.band_share, 0, sizeof(p.band_share));
+        if (use_bands)
+            std::memcpy(p.band_share, ctx->band_share[p.shard_rank].data(), sizeof(p.band_share));
         p.band_scope_sys = (ctx->fb_imported || i > 0 || ctx->shard_signals || std::getenv("RTM_BAND_SYS")) ? 1u : 0u;
         p.hit_tri = keep_hits ? ctx->d_hit_tri : nullptr;
         p.hit_t = keep_hits ? ctx->d_hit_t : nullptr;
@@ -886,8 +972,14 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
                                     shard_strips <= kVisitStripMask;
             if (want_order && shard_strips > 0)
             {
+                if (d.order_pending)
+                {
+                    CK(cudaStreamWaitEvent(d.stream, d.ev_order, 0)); // the order this frame follows / the buffers it reuses
+                    d.order_pending = false;
+                }
                 if (d.order_cap < shard_strips)
                 {
+                    CK(cudaStreamSynchronize(d.order_stream));
                     cudaFree(d.d_strip_cycles); cudaFree(d.d_fetch_order); cudaFree(d.d_order_scratch); cudaFree(d.d_visit_cycles);
                     d.d_strip_cycles = d.d_fetch_order = d.d_order_scratch = d.d_visit_cycles = nullptr;
                     d.order_cap = 0;
@@ -912,23 +1004,40 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
             else
                 d.order_valid = false;
         }
-        const int per_sm = std::max(1, trace_tiles_max_blocks_per_sm(f->variant, keep_hits, ctx->counting, (int) p.occ_mode, threads,
-                                                                       trace_tiles_smem_bytes(f->spp, p.occ_smem_words)));
+        const size_t smem_bytes = trace_tiles_smem_bytes(f->spp, p.occ_smem_words);
+        const std::vector<long long> okey = { (long long) f->variant, keep_hits, ctx->counting, (long long) p.occ_mode, threads,
+                                              (long long) smem_bytes };
+        if (okey != d.occupancy_key)
+        {
+            d.blocks_per_sm = std::max(1, trace_tiles_max_blocks_per_sm(f->variant, keep_hits, ctx->counting, (int) p.occ_mode,
+                                                                        threads, smem_bytes));
+            d.occupancy_key = okey;
+        }
+        const int per_sm = d.blocks_per_sm;
         const uint64_t my_strips = (total + p.shard_world - 1) / p.shard_world;
         const uint64_t want = (my_strips + (threads / 32) - 1) / (threads / 32);
         const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) d.sm_count * per_sm, want));
+        if (i == 0)
+            ctx->t_launching_ms = ms_since(ctx->t_enter);
         CK(cudaEventRecord(d.ev_begin, d.stream));
         if (total)
         {
             launch_trace_tiles(p, f->variant, keep_hits, ctx->counting, blocks, threads, d.stream);
             ctx->launches++;
         }
+        if (i == 0)
+            ctx->t_launched_ms = ms_since(ctx->t_enter);
         CK(cudaEventRecord(d.ev_end, d.stream));
+        CK(cudaMemcpyAsync(d.h_cancel_seen, d.d_cancel, sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
         if (p.visit_cycles && total)
         {
             // this frame's strip costs -> next frame's visiting order (off the timed kernel)
+            CK(cudaEventRecord(d.ev_traced, d.stream));
+            CK(cudaStreamWaitEvent(d.order_stream, d.ev_traced, 0));
             launch_build_strip_order(d.d_visit_cycles, p.fetch_order != nullptr, d.d_strip_cycles, (uint32_t) d.order_signature[10],
-                                     split_parts, d.d_cost_sum, d.d_order_scratch, d.d_visit_total, d.d_fetch_order, d.stream);
+                                     split_parts, d.d_cost_sum, d.d_order_scratch, d.d_visit_total, d.d_fetch_order, d.order_stream);
+            CK(cudaEventRecord(d.ev_order, d.order_stream));
+            d.order_pending = true;
             ctx->launches += 5;
             d.order_valid = true;
         }
@@ -971,14 +1080,14 @@ int cuda_trace_sync(cuda_trace_ctx *ctx)
     {
         CK(cudaSetDevice(d.ordinal));
         CK(cudaStreamSynchronize(d.stream));
+        if (ctx->marks_armed)
+            ctx->t_traced_ms = ms_since(ctx->t_enter);
         if (d.frame_pending)
         {
             float ms = 0.0f;
             CK(cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
             ms_max = std::max(ms_max, ms);
-            uint32_t flag = 0;
-            CK(cudaMemcpy(&flag, d.d_cancel, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-            cancelled = cancelled || flag != 0;
+            cancelled = cancelled || *(volatile uint32_t *) d.h_cancel_seen != 0; // copied out behind the kernel
             d.frame_pending = false;
             any = true;
         }
@@ -987,6 +1096,8 @@ int cuda_trace_sync(cuda_trace_ctx *ctx)
     {
         CK(cudaSetDevice(ctx->dev[0].ordinal));
         CK(cudaStreamSynchronize(ctx->dev[0].copy_stream));
+        if (ctx->marks_armed)
+            ctx->t_copied_ms = ms_since(ctx->t_enter);
         ctx->copy_pending = false;
     }
     if (any)
@@ -1045,14 +1156,31 @@ int cuda_trace_read_framebuffer(cuda_trace_ctx *ctx, uint32_t *host_bgra)
 int cuda_trace_tiles(cuda_trace_ctx *ctx, const cuda_trace_frame *frame, const cuda_trace_tile_rect *tiles,
                      uint32_t n_tiles, uint32_t *host_bgra)
 {
+    if (!ctx)
+        return CUDA_TRACE_ERR_ARG;
+    ctx->t_enter = std::chrono::steady_clock::now();
     int rc = tiles_async_impl(ctx, frame, tiles, n_tiles, host_bgra);
     if (rc)
         return rc;
+    ctx->t_submitted_ms = ms_since(ctx->t_enter);
     const bool overlapped = ctx->copy_pending; // the bands are already on their way to host_bgra
-    if ((rc = cuda_trace_sync(ctx)))
+    ctx->marks_armed = true;
+    rc = cuda_trace_sync(ctx);
+    ctx->marks_armed = false;
+    if (rc)
         return rc;
     if (host_bgra && !overlapped)
-        return cuda_trace_read_framebuffer(ctx, host_bgra);
+        rc = cuda_trace_read_framebuffer(ctx, host_bgra);
+    ctx->t_return_ms = ms_since(ctx->t_enter);
+    return rc;
+}
+
+int cuda_trace_last_call_timing(cuda_trace_ctx *ctx, double ms[7])
+{
+    if (!ctx || !ms)
+        return CUDA_TRACE_ERR_ARG;
+    ms[0] = ctx->t_submitted_ms; ms[1] = ctx->t_traced_ms; ms[2] = ctx->t_copied_ms; ms[3] = ctx->t_return_ms;
+    ms[4] = ctx->t_prepared_ms; ms[5] = ctx->t_launching_ms; ms[6] = ctx->t_launched_ms;
     return 0;
 }
 
@@ -1327,6 +1455,8 @@ int cuda_trace_download_strip_cycles(cuda_trace_ctx *ctx, uint32_t *cycles, uint
     if (rc)
         return rc;
     DeviceState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.ordinal));
+    CK(cudaStreamSynchronize(d.order_stream));
     *count = (d.order_valid && d.order_signature.size() > 10) ? d.order_signature[10] : 0;
     const uint64_t n = std::min<uint64_t>(*count, capacity);
     if (n)

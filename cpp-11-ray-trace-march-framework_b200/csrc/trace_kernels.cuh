@@ -63,8 +63,12 @@ struct TraceParams
     uint32_t *strip_counter;           // dynamic strip scheduler (zeroed before launch)
     const uint32_t *cancel;            // non-zero => stop fetching strips
     uint32_t *framebuffer;             // width * height, row 0 = y 0 (may be a peer / IPC pointer)
-    uint32_t *band_done;               // per row band: strips finished so far (monotone across frames; lives behind the
-                                       // framebuffer, so peers / other ranks reach it through the same mapping) or null
+    uint32_t *band_done;               // per row band: GPUs whose share of the band is finished (monotone across frames;
+                                       // lives behind the framebuffer, so peers / other ranks reach it through the
+                                       // same mapping) or null
+    uint32_t *band_local;              // per row band: pieces of strips THIS GPU has finished in this frame (local memory);
+                                       // null = single GPU, band_done counts pieces directly
+    uint32_t band_share[kMaxBands];    // ... and how many that makes when its share of the band is complete
     uint32_t band_rows;                // rows per band
     uint32_t band_scope_sys;           // 1: counters / pixels may live on another GPU (system-scope release), 0: local
     uint32_t *hit_tri;                 // optional per-sample records (KEEP_HITS)

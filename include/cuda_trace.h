@@ -211,6 +211,11 @@ int cuda_trace_qmc_cranley_patterson(cuda_trace_ctx *ctx, const double *x, doubl
 int cuda_trace_set_counting(cuda_trace_ctx *ctx, int enable);
 int cuda_trace_get_counters(cuda_trace_ctx *ctx, cuda_trace_counters *out);
 
+/* Host-clock marks of the last cuda_trace_tiles call, in ms since its entry: [0] work submitted, [1] trace stream
+ * drained, [2] read-back copies drained (overlapped mode), [3] return, [4] host set-up done, [5] / [6] before /
+ * after the launch of the first device's trace kernel.  Diagnostics for the end-to-end figure. */
+int cuda_trace_last_call_timing(cuda_trace_ctx *ctx, double ms[7]);
+
 /* Scheduler diagnostics: SM cycles each strip of the last frame took on device 0, in this shard's strip order
  * (the input of the cost-ordered scheduling, csrc/schedule.cu).  *count = strips recorded (0 when the last frame
  * ran without cost recording -- see RTM_COST_ORDER); at most `capacity` values are written. */

@@ -6,6 +6,7 @@ timeout 1200 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -
 for WL in killeroo4k C4; do
 for N in 1 2 4 8; do
   [ $N -gt $NG ] && continue
+  [ "$WL" = C4 ] && [ $N -ne 1 ] && [ $N -ne $NG ] && continue   # C4: end points only
   if [ $N -eq 1 ]; then
     timeout 600 python bench.py --workload $WL --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_${WL}_n$N.json 2>$OUT/bench_${WL}_n$N.err
   else
