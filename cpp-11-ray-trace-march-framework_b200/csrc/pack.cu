@@ -147,6 +147,35 @@ inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned) ((n
 
 } // namespace
 
+// Primary rays share their origin, so everything in the Moeller-Trumbore test (triangle.h:15-107) that does not
+// involve the direction is the same for every ray of a frame: tvec = orig - v0, qvec = tvec x e1, e2 . qvec.
+// Computed here once per camera position with the very expressions of the per-ray test (same operand order, no
+// contraction), so the per-ray results stay bit-identical: {tvec, tri}, {e1}, {e2}, {qvec, e2 . qvec}.
+__global__ void origin_relative_records_kernel(const float4 *__restrict__ cell_tris, uint64_t num_refs, float ox, float oy,
+                                               float oz, float4 *__restrict__ rel)
+{
+    const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= num_refs)
+        return;
+    const float4 ra = cell_tris[3 * k + 0], rb = cell_tris[3 * k + 1], rc = cell_tris[3 * k + 2];
+    const float tx = ox - ra.x, ty = oy - ra.y, tz = oz - ra.z;
+    const float qx = ty * rb.z - tz * rb.y;
+    const float qy = tz * rb.x - tx * rb.z;
+    const float qz = tx * rb.y - ty * rb.x;
+    rel[4 * k + 0] = make_float4(tx, ty, tz, ra.w);
+    rel[4 * k + 1] = rb;
+    rel[4 * k + 2] = rc;
+    rel[4 * k + 3] = make_float4(qx, qy, qz, rc.x * qx + rc.y * qy + rc.z * qz);
+}
+
+void launch_origin_relative_records(const float4 *cell_tris, uint64_t num_refs, const float origin[3], float4 *rel,
+                                    cudaStream_t stream)
+{
+    if (num_refs)
+        origin_relative_records_kernel<<<blocks_for(num_refs, 256), 256, 0, stream>>>(cell_tris, num_refs, origin[0], origin[1],
+                                                                                      origin[2], rel);
+}
+
 void launch_pack_cell_tris(const float *vtx, const uint32_t *tri, const uint32_t *tri_index, uint64_t num_refs,
                            float4 *cell_tris, float4 *cell_tris_b, cudaStream_t stream)
 {

@@ -492,11 +492,14 @@ int occupancy_one(int occ_mode, int threads, size_t smem)
 
 } // namespace
 
+// variant 2 (origin-relative records) exists without the counting instrumentation only
 #define RTM_DISPATCH(FN, ...)                                                                    \
     do {                                                                                         \
-        const int key = (variant ? 4 : 0) | (keep_hits ? 2 : 0) | (count ? 1 : 0);               \
+        const int key = (int) (variant == kVariantMTRel && count ? 0u : variant) * 4 | (keep_hits ? 2 : 0) | (count ? 1 : 0); \
         switch (key)                                                                             \
         {                                                                                        \
+            case 8: return FN<2, false, false>(__VA_ARGS__);                                     \
+            case 10: return FN<2, true, false>(__VA_ARGS__);                                     \
             case 0: return FN<0, false, false>(__VA_ARGS__);                                     \
             case 1: return FN<0, false, true>(__VA_ARGS__);                                      \
             case 2: return FN<0, true, false>(__VA_ARGS__);                                      \

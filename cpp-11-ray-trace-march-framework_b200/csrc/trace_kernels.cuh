@@ -38,6 +38,10 @@ constexpr int kTraceMaxThreads = 1024; // launch bound (caps the kernel at 64 re
 //      grids of configs C2-C4): the test is a single LDS.U8 without shift / mask arithmetic
 enum { kOccGlobalBits = 0, kOccSmemBits = 1, kOccSmemBytes = 2 };
 
+// Kernel-side intersection variants: 0 / 1 are the ABI's (Moeller-Trumbore, plane + barycentric); 2 is
+// Moeller-Trumbore on origin-relative records (GridDev::cell_tris_rel) -- the launcher's choice for primary rays
+enum { kVariantMT = 0, kVariantBary = 1, kVariantMTRel = 2 };
+
 struct TraceParams
 {
     GridDev grid;
@@ -107,6 +111,8 @@ size_t strip_order_scratch_words(uint32_t n);
 size_t strip_order_capacity(uint32_t n, uint32_t parts);
 
 // scene packing (pack.cu)
+void launch_origin_relative_records(const float4 *cell_tris, uint64_t num_refs, const float origin[3], float4 *rel,
+                                    cudaStream_t stream);
 void launch_pack_cell_tris(const float *vtx, const uint32_t *tri, const uint32_t *tri_index, uint64_t num_refs,
                            float4 *cell_tris, float4 *cell_tris_b, cudaStream_t stream);
 void launch_pack_normals(const float *vtx, const uint32_t *tri, uint32_t num_tri, float4 *tri_normals,

@@ -197,6 +197,47 @@ def test_occupancy_map_modes(cuda_trace, port, scene_data, monkeypatch, mode, na
     assert np.array_equal(cuda_trace.trace_tiles(f2), o["bgra"])
 
 
+@pytest.mark.parametrize("mode", ["0", "2"])
+@pytest.mark.parametrize("name,spp", [("killeroo", 4), ("cornell", 16), ("head", 1), ("dwarf_hand_blob", 64)])
+def test_origin_relative_records(port, scene_data, monkeypatch, mode, name, spp):
+    """Frames of 16 M rays and more run Moeller-Trumbore on records relative to the camera position
+    (tvec, qvec and e2.qvec precomputed once per camera, csrc/pack.cu).  Forced on here for small frames so that
+    the per-sample t / u / v can be compared bit for bit with the oracle, in two occupancy modes, before and after
+    the camera moves (the records are rebuilt), and against the plain records (forced off)."""
+    capi = pkg("capi")
+    sd = scene_data(name)
+    w, h = 192, 128
+    ps = port.scene(sd.vtx, sd.tri, 64)
+    cam2 = np.array(sd.cam16, np.float32).copy()
+    cam2[12:15] += np.array([0.03, -0.02, 0.05], np.float32)  # Matrix44f translation row = camera origin
+    outs = {}
+    for rel in ("2", "0"):
+        monkeypatch.setenv("RTM_REL_RECORDS", rel)
+        monkeypatch.setenv("RTM_OCC_MODE", mode)
+        monkeypatch.setenv("RTM_THREADS", "1024" if mode != "0" else "256")
+        ct = capi.CudaTrace(1)
+        ct.upload_scene(sd.vtx, sd.tri, 64)
+        fov_xs, aspect = port.camera_constants(sd.fov, w, h)
+        for k, cam in enumerate((sd.cam16, cam2, sd.cam16)):
+            f = ct.make_frame(w, h, spp, cam, fov_xs, aspect, keep_hits=True)
+            img = ct.trace_tiles(f)
+            tri, t, u, v = ct.download_hits(w, h, spp)
+            outs[(rel, k)] = (img.copy(), tri, t, u, v)
+            plain = ct.trace_tiles(ct.make_frame(w, h, spp, cam, fov_xs, aspect))  # non-instrumented instantiation
+            assert np.array_equal(plain, img)
+        ct.close()
+    for k, cam in enumerate((sd.cam16, cam2)):
+        o = ps.render(cam, sd.fov, w, h, spp, want_hits=True, want_tuv=True)
+        for rel in ("2", "0"):
+            img, tri, t, u, v = outs[(rel, k)]
+            assert np.array_equal(tri, o["tri"]) and np.array_equal(img, o["bgra"]), (rel, k)
+            for got, key in ((t, "t"), (u, "u"), (v, "v")):
+                assert np.array_equal(got.view(np.uint32), o[key].view(np.uint32)), (rel, k, key)
+    for rel in ("2", "0"):  # back at the first camera
+        for a, b in zip(outs[(rel, 2)], outs[(rel, 0)]):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_brute_force_self_check(cuda_trace, ref, port, scene_data):
     """Renderer::IntersectBruteForce on the device: bit-exact against the reference's own brute force, and
     -- the author's cross-check -- equal to the grid result except where the grid's in-cell rule decides."""
