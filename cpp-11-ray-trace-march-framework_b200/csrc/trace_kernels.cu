@@ -107,7 +107,17 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
     Counters cnt = { 0, 0, 0, 0 };
 
     const uint32_t slots = p.strip_w * p.strip_h;
-    uint32_t pend_band = 0, pend_count = 0; // finished pieces not yet published (see the band publication below)
+    // finished pieces not yet published (see the band publication below): lane b holds those of row band b
+    // (kMaxBands == 32), slot 0 of s_pend_total their warp-uniform sum.  In shared memory, touched once per
+    // strip: as registers they would be live across the whole traversal, which is at its 64-register cap
+    __shared__ uint32_t s_pend[BANDS ? kTraceMaxThreads : 1], s_pend_total[BANDS ? kTraceMaxThreads / 32 : 1];
+    if (BANDS)
+    {
+        s_pend[threadIdx.x] = 0;
+        if (lane == 0)
+            s_pend_total[threadIdx.x >> 5] = 0;
+        __syncwarp();
+    }
     const uint32_t n_visits = p.fetch_order ? __ldg(p.visit_total) : p.shard_strips;
     const uint32_t part_slots = slots / p.split_parts;
     for (;;)
@@ -244,34 +254,33 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         // guard every vote of the traversal with a divergence check, +3 instructions per triangle test)
         if (BANDS && p.band_done)
         {
-            // Publish "these strips' pixels are stored" per row band.  Finished strips are batched
-            // per warp (same band, up to 8) because the publication is a release: a warp barrier
-            // orders every lane's pixel stores before lane 0's release-increment, whose fence is
-            // the expensive part (system scope when the counter lives on another GPU / process).
-            // The host's copy stream waits on these counters and ships each row band to the host
-            // while later bands are still being traced.
+            // Publish "these strips' pixels are stored" per row band.  The publication is a release: a warp
+            // barrier orders every lane's pixel stores before the release-increments, whose fence is the
+            // expensive part -- so finished pieces are collected per warp, lane b keeping the count of band b
+            // (consecutive strips of one warp are thousands of strip ids apart and rarely share a band), and
+            // published eight strips at a time: one fence, then one increment per band touched.
+            // The host's copy stream waits on these counters and ships each row band to the host while later
+            // bands are still being traced.
             const uint32_t b0 = by0 / p.band_rows, b1 = (by0 + bh - 1) / p.band_rows;
-            const bool flush = pend_count && (pend_band != b0 || pend_count >= 8u * p.split_parts);
+            // (a strip straddling two bands counts in both)
+            const uint32_t my_pend = s_pend[threadIdx.x] + (lane == b0 ? units : 0u) + ((b1 != b0 && lane == b1) ? units : 0u);
+            const uint32_t pend_total = s_pend_total[threadIdx.x >> 5] + units;
+            const bool flush = pend_total >= 8u * p.split_parts;
             __syncwarp(); // unconditional, at the top level of the strip loop (a barrier under a
                           // data-dependent branch would make the compiler guard every vote in the loop)
+            if (flush && my_pend)
+                release_add(p, lane, my_pend);
+            s_pend[threadIdx.x] = flush ? 0u : my_pend;
             if (lane == 0)
-            {
-                if (flush)
-                    release_add(p, pend_band, pend_count);
-                if (b1 != b0)
-                    release_add(p, b1, units); // a strip straddling two bands counts in both
-            }
-            if (flush)
-                pend_count = 0;
-            pend_band = b0;
-            pend_count += units;
+                s_pend_total[threadIdx.x >> 5] = flush ? 0u : pend_total;
+            __syncwarp();
         }
     }
     if (BANDS && p.band_done)
     {
         __syncwarp();
-        if (lane == 0 && pend_count)
-            release_add(p, pend_band, pend_count);
+        if (s_pend[threadIdx.x])
+            release_add(p, lane, s_pend[threadIdx.x]);
     }
 
     if (COUNT)
