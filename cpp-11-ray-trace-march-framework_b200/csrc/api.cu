@@ -1039,6 +1039,16 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
         const uint64_t my_strips = (total + p.shard_world - 1) / p.shard_world;
         const uint64_t want = (my_strips + (threads / 32) - 1) / (threads / 32);
         const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) d.sm_count * per_sm, want));
+        {
+            // How many finished strips a warp collects before it publishes them to the band counters: the fence
+            // costs ~1 us, but a held-back strip delays its band's read-back -- at most 1/16 of a warp's share
+            // of the frame (8 strips for a whole 4K frame on one GPU, every strip for an eighth of it)
+            const uint64_t warps = (uint64_t) blocks * (threads / 32);
+            uint64_t hold = std::min<uint64_t>(8, std::max<uint64_t>(1, my_strips / std::max<uint64_t>(1, warps * 16)));
+            if (const char *e = std::getenv("RTM_BAND_FLUSH")) // tuning override (experiments only): strips held, 1..8
+                hold = (uint64_t) std::min(8, std::max(1, std::atoi(e)));
+            p.band_flush_units = (uint32_t) hold * split_parts;
+        }
         if (i == 0)
             ctx->t_launching_ms = ms_since(ctx->t_enter);
         CK(cudaEventRecord(d.ev_begin, d.stream));

@@ -258,14 +258,14 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
             // barrier orders every lane's pixel stores before the release-increments, whose fence is the
             // expensive part -- so finished pieces are collected per warp, lane b keeping the count of band b
             // (consecutive strips of one warp are thousands of strip ids apart and rarely share a band), and
-            // published eight strips at a time: one fence, then one increment per band touched.
+            // published a few strips at a time (band_flush_units): one fence, then one increment per band touched.
             // The host's copy stream waits on these counters and ships each row band to the host while later
             // bands are still being traced.
             const uint32_t b0 = by0 / p.band_rows, b1 = (by0 + bh - 1) / p.band_rows;
             // (a strip straddling two bands counts in both)
             const uint32_t my_pend = s_pend[threadIdx.x] + (lane == b0 ? units : 0u) + ((b1 != b0 && lane == b1) ? units : 0u);
             const uint32_t pend_total = s_pend_total[threadIdx.x >> 5] + units;
-            const bool flush = pend_total >= 8u * p.split_parts;
+            const bool flush = pend_total >= p.band_flush_units;
             __syncwarp(); // unconditional, at the top level of the strip loop (a barrier under a
                           // data-dependent branch would make the compiler guard every vote in the loop)
             if (flush && my_pend)

@@ -74,6 +74,7 @@ struct TraceParams
                                        // null = single GPU, band_done counts pieces directly
     uint32_t band_share[kMaxBands];    // ... and how many that makes when its share of the band is complete
     uint32_t band_rows;                // rows per band
+    uint32_t band_flush_units;         // a warp publishes its finished pieces once it holds this many
     uint32_t band_scope_sys;           // 1: counters / pixels may live on another GPU (system-scope release), 0: local
     uint32_t *hit_tri;                 // optional per-sample records (KEEP_HITS)
     float *hit_t, *hit_u, *hit_v;
