@@ -16,6 +16,9 @@ VARIANT_MT = 0
 VARIANT_BARY = 1
 FLAG_GAMMA = 1
 FLAG_KEEP_HITS = 2
+FLAG_ORTHO = 4              # camera.h:25-36; the frame's fov_xs then carries the width of the viewing volume
+FLAG_SHADE_FACE_NORMAL = 8  # renderer.cpp:116
+FLAG_SHADE_DEPTH = 16       # renderer.cpp:118
 
 _F32P = C.POINTER(C.c_float)
 _U32P = C.POINTER(C.c_uint32)
@@ -215,11 +218,15 @@ class CudaTrace:
 
     # -- frames
     @staticmethod
-    def make_frame(width, height, spp, cam16, fov_xs, aspect, variant=VARIANT_MT, gamma=True, keep_hits=False):
+    def make_frame(width, height, spp, cam16, fov_xs, aspect, variant=VARIANT_MT, gamma=True, keep_hits=False,
+                   ortho_width=None, shade_mode=0):
+        """ortho_width: orthographic camera of that width (replaces fov_xs); shade_mode 1 / 2: face normal / depth"""
         f = Frame()
         f.width, f.height, f.spp, f.variant = width, height, spp, variant
-        f.flags = (FLAG_GAMMA if gamma else 0) | (FLAG_KEEP_HITS if keep_hits else 0)
-        f.fov_xs, f.aspect = float(fov_xs), float(aspect)
+        f.flags = ((FLAG_GAMMA if gamma else 0) | (FLAG_KEEP_HITS if keep_hits else 0) |
+                   (FLAG_ORTHO if ortho_width is not None else 0) |
+                   (FLAG_SHADE_FACE_NORMAL if shade_mode == 1 else 0) | (FLAG_SHADE_DEPTH if shade_mode == 2 else 0))
+        f.fov_xs, f.aspect = float(fov_xs if ortho_width is None else ortho_width), float(aspect)
         cam16 = np.asarray(cam16, np.float32).reshape(16)
         for i in range(16):
             f.cam_mat[i] = float(cam16[i])

@@ -188,6 +188,7 @@ GridDev grid_dev(const cuda_trace_ctx *ctx, const DeviceState& d)
     g.cell_tris_b = d.d_cell_tris_b;
     g.cell_tris_rel = d.d_cell_tris_rel;
     g.tri_normals = d.d_tri_normals;
+    g.tri = d.d_tri;
     return g;
 }
 
@@ -868,12 +869,24 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
 
         TraceParams p;
         p.grid = grid_dev(ctx, d);
+        const bool ortho = (f->flags & CUDA_TRACE_FLAG_ORTHO) != 0;
         for (int r = 0; r < 3; r++)
         {
             for (int c = 0; c < 3; c++)
                 p.cam.m[r][c] = f->cam_mat[r * 4 + c];
-            p.cam.origin[r] = f->cam_mat[12 + r];
+            // perspective: origin = Transf4x4(Vec3f(0)) (camera.h:43, lin_alg.h:518-535), all four terms kept
+            // (a -0 translation comes out as +0); orthographic: the raw row, used per ray
+            const float zero = 0.0f, m3 = f->cam_mat[12 + r];
+            p.cam.origin[r] = ortho ? m3 : zero * f->cam_mat[0 + r] + zero * f->cam_mat[4 + r] + zero * f->cam_mat[8 + r] + m3;
         }
+        p.cam.ortho = ortho ? 1u : 0u;
+        {
+            // camera.h:28-31: const float width = width_or_hfov, height = float(width) / aspect; half = x / 2.0
+            const float ow = f->fov_xs, oh = ow / f->aspect;
+            p.cam.ortho_half_w = (float) ((double) ow / 2.0);
+            p.cam.ortho_half_h = (float) ((double) oh / 2.0);
+        }
+        p.shade_mode = (f->flags & CUDA_TRACE_FLAG_SHADE_FACE_NORMAL) ? 1u : ((f->flags & CUDA_TRACE_FLAG_SHADE_DEPTH) ? 2u : 0u);
         p.cam.fov_xs = f->fov_xs;
         p.cam.aspect = f->aspect;
         p.cam.width_f = (float) f->width;
@@ -1024,7 +1037,12 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
         // of 1080p / 4 spp, -10 % on 512^2 / 1 spp, which is launch- and cold-miss-bound (the records are 64 B, not 48)
         const bool rel_fits = ctx->desc.num_refs <= (4ull << 20) &&
                               ((uint64_t) f->width * f->height * f->spp >= (16ull << 20) || ctx->rel_records_forced);
-        const uint32_t kvariant = (f->variant == kVariantMT && !ctx->counting && ctx->rel_records && rel_fits)
+        const bool alternates = ortho || p.shade_mode != 0;
+        if (alternates && ctx->counting)
+            return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: the work counters are not available with the orthographic "
+                                                 "camera / shading alternates");
+        const uint32_t kvariant = alternates ? (uint32_t) kVariantMTAlt + f->variant
+                                  : (f->variant == kVariantMT && !ctx->counting && ctx->rel_records && rel_fits)
                                       ? (uint32_t) kVariantMTRel : f->variant;
         const size_t smem_bytes = trace_tiles_smem_bytes(f->spp, p.occ_smem_words);
         const std::vector<long long> okey = { (long long) kvariant, keep_hits, ctx->counting, (long long) p.occ_mode, threads,

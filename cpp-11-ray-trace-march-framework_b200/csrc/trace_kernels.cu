@@ -27,12 +27,14 @@ __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const void 
 {
     float3 o, d;
     const float2 off = smp[valid ? s : 0];
-    generate_ray(p.cam, px, py, off.x, off.y, o, d);
+    constexpr bool ALT = VARIANT >= kVariantMTAlt;
+    constexpr int TRI_VARIANT = ALT ? VARIANT - kVariantMTAlt : VARIANT;
+    generate_ray<ALT>(p.cam, px, py, off.x, off.y, o, d);
     Hit hit;
     hit.t = hit.u = hit.v = 0.0f;
     hit.tri = 0xFFFFFFFFu;
     if (COUNT && valid) cnt->rays++;
-    const bool is_hit = warp_grid_intersect<VARIANT, COUNT, OCC_MODE, RCP_GUARD>(p.grid, s_occ, o, d, valid, hit, cnt);
+    const bool is_hit = warp_grid_intersect<TRI_VARIANT, COUNT, OCC_MODE, RCP_GUARD>(p.grid, s_occ, o, d, valid, hit, cnt);
     if (COUNT && is_hit) cnt->hits++;
     if (KEEP_HITS && valid)
     {
@@ -44,7 +46,7 @@ __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const void 
     }
     float3 rgb = make_float3(0.0f, 0.0f, 0.0f);
     if (valid)
-        rgb = shade_sample(p.grid, is_hit, hit, py, p.cam.height_f);
+        rgb = shade_sample<ALT>(p.grid, is_hit, hit, py, p.cam.height_f, p.shade_mode);
     return rgb;
 }
 
@@ -455,7 +457,7 @@ void launch_instance(const TraceParams& p, int grid_blocks, int threads, size_t 
 template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE>
 void launch_mode(const TraceParams& p, int grid_blocks, int threads, size_t smem, cudaStream_t stream)
 {
-    constexpr bool kPlain = !KEEP_HITS && !COUNT;
+    constexpr bool kPlain = !KEEP_HITS && !COUNT && VARIANT < kVariantMTAlt; // the alternates: one instantiation each
     if (kPlain)
     {
         const bool guard = p.rcp_guard != 0, bands = p.band_done != nullptr;
@@ -501,7 +503,7 @@ int occupancy_one(int occ_mode, int threads, size_t smem)
 
 } // namespace
 
-// variant 2 (origin-relative records) exists without the counting instrumentation only
+// variants 2 (origin-relative records) and 3 / 4 (alternates) exist without the counting instrumentation only
 #define RTM_DISPATCH(FN, ...)                                                                    \
     do {                                                                                         \
         const int key = (int) (variant == kVariantMTRel && count ? 0u : variant) * 4 | (keep_hits ? 2 : 0) | (count ? 1 : 0); \
@@ -509,6 +511,10 @@ int occupancy_one(int occ_mode, int threads, size_t smem)
         {                                                                                        \
             case 8: return FN<2, false, false>(__VA_ARGS__);                                     \
             case 10: return FN<2, true, false>(__VA_ARGS__);                                     \
+            case 12: case 13: return FN<3, false, false>(__VA_ARGS__);                           \
+            case 14: case 15: return FN<3, true, false>(__VA_ARGS__);                            \
+            case 16: case 17: return FN<4, false, false>(__VA_ARGS__);                           \
+            case 18: case 19: return FN<4, true, false>(__VA_ARGS__);                            \
             case 0: return FN<0, false, false>(__VA_ARGS__);                                     \
             case 1: return FN<0, false, true>(__VA_ARGS__);                                      \
             case 2: return FN<0, true, false>(__VA_ARGS__);                                      \

@@ -40,7 +40,9 @@ enum { kOccGlobalBits = 0, kOccSmemBits = 1, kOccSmemBytes = 2 };
 
 // Kernel-side intersection variants: 0 / 1 are the ABI's (Moeller-Trumbore, plane + barycentric); 2 is
 // Moeller-Trumbore on origin-relative records (GridDev::cell_tris_rel) -- the launcher's choice for primary rays
-enum { kVariantMT = 0, kVariantBary = 1, kVariantMTRel = 2 };
+// 3 / 4 are 0 / 1 with the reference's alternates compiled in (orthographic camera, face-normal and depth shading:
+// CameraDev::ortho, TraceParams::shade_mode) -- separate instantiations so that the live path does not carry them
+enum { kVariantMT = 0, kVariantBary = 1, kVariantMTRel = 2, kVariantMTAlt = 3, kVariantBaryAlt = 4 };
 
 struct TraceParams
 {
@@ -48,6 +50,7 @@ struct TraceParams
     CameraDev cam;
     uint32_t width, height, spp;
     uint32_t gamma;
+    uint32_t shade_mode;               // 0 interpolated vertex normal (live), 1 face normal, 2 depth (rt_device.cuh)
     const float2 *smp;                 // sample table, spp entries (K2)
     uint32_t occ_mode;                 // kOccGlobalBits / kOccSmemBits / kOccSmemBytes (warp_trace.cuh)
     uint32_t occ_smem_words;           // 32-bit words of the occupancy map staged in shared memory

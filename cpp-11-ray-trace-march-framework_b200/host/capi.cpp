@@ -173,6 +173,13 @@ double rtm_renderer_render(void *h, uint32 width, uint32 height, uint32 spp, uin
         return -1.0;
     }
 }
+void rtm_renderer_set_alternates(void *h, float ortho_width, uint32 shade_mode)
+{
+    Renderer *r = static_cast<HostRenderer *>(h)->renderer.get();
+    r->WaitRendering();
+    r->SetOrthographicWidth(ortho_width);
+    r->SetShadingMode(shade_mode);
+}
 float rtm_renderer_last_kernel_ms(void *h) { return static_cast<HostRenderer *>(h)->renderer->GetLastKernelMilliseconds(); }
 void rtm_renderer_save_bmp(void *h, const char *filename) { static_cast<HostRenderer *>(h)->renderer->SaveToBMP(filename); }
 void *rtm_renderer_device_context(void *h)

@@ -52,6 +52,13 @@ void Renderer::RenderTiles(Tile * const *tiles, uint count)
     frame.variant = m_variant;
     frame.flags = m_gamma ? CUDA_TRACE_FLAG_GAMMA : 0u;
     CameraFrameConstants(fov, m_width, m_height, frame.fov_xs, frame.aspect);
+    if (m_ortho_width > 0.0f)
+    {
+        frame.flags |= CUDA_TRACE_FLAG_ORTHO;
+        frame.fov_xs = m_ortho_width; // width_or_hfov of camera.h:13
+    }
+    if (m_shade_mode == 1u) frame.flags |= CUDA_TRACE_FLAG_SHADE_FACE_NORMAL;
+    if (m_shade_mode == 2u) frame.flags |= CUDA_TRACE_FLAG_SHADE_DEPTH;
     std::memcpy(frame.cam_mat, cam_mat.m_mat, sizeof(frame.cam_mat));
 
     std::vector<cuda_trace_tile_rect> rects(count);

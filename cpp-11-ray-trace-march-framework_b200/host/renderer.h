@@ -26,6 +26,11 @@ public:
     // (triangle.h:210-226).  Gamma 1/2 is on by default like the reference's GAMMA_CORRECTION.
     void SetIntersectVariant(uint variant) { m_variant = variant ? 1u : 0u; }
     void SetGammaCorrection(bool on) { m_gamma = on; }
+    // The reference's other alternates (none reachable through its own API): GenerateRay's orthographic branch
+    // (camera.h:25-36; width of the viewing volume, 0 = perspective) and the two commented-out shading lines,
+    // 1: "Vec3f n = tri.n" (renderer.cpp:116), 2: "col += Vec3f(t / 3)" (renderer.cpp:118), 0: the live one
+    void SetOrthographicWidth(float width) { m_ortho_width = width; }
+    void SetShadingMode(uint mode) { m_shade_mode = mode <= 2u ? mode : 0u; }
     Scene * GetScene() { return m_scene.get(); }
     float GetLastKernelMilliseconds() const { return m_last_kernel_ms; }
     // The reference's sphere tracer (renderer.h:21 / renderer.cpp:24-41; protected and unused there): a one-ray
@@ -41,6 +46,8 @@ protected:
     uint m_sample_count = 16;
     uint m_variant = 0;
     bool m_gamma = true;
+    float m_ortho_width = 0.0f;
+    uint m_shade_mode = 0;
     float m_last_kernel_ms = 0.0f;
     uint32 *m_frame = nullptr;   // page-locked full-frame staging the device framebuffer is copied into
     size_t m_frame_pixels = 0;

@@ -42,6 +42,7 @@ def load_host_library():
         lib.rtm_renderer_device_context.argtypes = [C.c_void_p]
         lib.rtm_renderer_intersect.restype = C.c_int
         lib.rtm_renderer_intersect.argtypes = [C.c_void_p, _F32P, _F32P, _F32P, _U32P]
+        lib.rtm_renderer_set_alternates.argtypes = [C.c_void_p, C.c_float, C.c_uint32]
         lib.rtm_renderer_ray_march.restype = C.c_int
         lib.rtm_renderer_ray_march.argtypes = [C.c_void_p, _F32P, _F32P, _F32P]
         lib.rtm_renderer_grid_info.argtypes = [C.c_void_p, _U32P, _F32P, _F32P, _F32P, C.POINTER(C.c_uint64)]
@@ -84,6 +85,10 @@ class HostRenderer:
         if sec < 0:
             raise RuntimeError("render failed: " + self.lib.rtm_last_error().decode())
         return sec, out
+
+    def set_alternates(self, ortho_width=0.0, shade_mode=0):
+        """Renderer::SetOrthographicWidth / SetShadingMode (0 width = perspective; mode 0 = the live shading)."""
+        self.lib.rtm_renderer_set_alternates(self.h, float(ortho_width), int(shade_mode))
 
     def last_kernel_ms(self):
         return float(self.lib.rtm_renderer_last_kernel_ms(self.h))

@@ -43,6 +43,11 @@ typedef enum cuda_trace_status
 
 #define CUDA_TRACE_FLAG_GAMMA     1u /* renderer.cpp:125-131 (#define GAMMA_CORRECTION); on in the reference */
 #define CUDA_TRACE_FLAG_KEEP_HITS 2u /* also record per-sample tri_idx,t,u,v (cuda_trace_download_hits)      */
+/* The alternates the reference keeps next to its live lines; none is set by a reference caller */
+#define CUDA_TRACE_FLAG_ORTHO             4u  /* GenerateRay's orthographic branch (camera.h:25-36): the frame's
+                                               * fov_xs field then carries the WIDTH of the viewing volume      */
+#define CUDA_TRACE_FLAG_SHADE_FACE_NORMAL 8u  /* "Vec3f n = tri.n;"      (renderer.cpp:116, commented out)      */
+#define CUDA_TRACE_FLAG_SHADE_DEPTH       16u /* "col += Vec3f(t / 3);"  (renderer.cpp:118, commented out)      */
 
 /* Per-frame inputs of Renderer::RenderTile (renderer.cpp:63-72,91-99): frame size (Framebuffer::
  * m_width/m_height), sample count (Renderer::m_sample_count), Scene::GetCameraParameters().

@@ -222,6 +222,14 @@ class RefRenderer:
         self.lib.ref_generate_rays(self.h, width, height, spp, y_begin, y_end, _p(o, _F32P), _p(d, _F32P))
         return o, d
 
+    def generate_rays_ortho(self, width, height, spp, y_begin, y_end, ortho_width):
+        shape = (y_end - y_begin, width, spp, 3)
+        o, d = np.empty(shape, np.float32), np.empty(shape, np.float32)
+        self.lib.ref_generate_rays_ortho.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                     C.c_float, _F32P, _F32P]
+        self.lib.ref_generate_rays_ortho(self.h, width, height, spp, y_begin, y_end, ortho_width, _p(o, _F32P), _p(d, _F32P))
+        return o, d
+
     def grid(self):
         """-> dict(dim, aabb_min, aabb_max, cell_wdh, inv_cell_wdh, cell_offset u64, tri_index u32)"""
         dim = np.zeros(3, np.uint32)
@@ -249,6 +257,10 @@ class RefRenderer:
 
 
 # ----------------------------------------------------------------------------------------- port
+class _RenderOptions(C.Structure):
+    _fields_ = [("ortho", C.c_int), ("ortho_width", C.c_float), ("shade_mode", C.c_int)]
+
+
 class _Grid(C.Structure):
     _fields_ = [("dim", C.c_uint32 * 3), ("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3),
                 ("cell_wdh", C.c_float), ("inv_cell_wdh", C.c_float), ("num_cells", C.c_uint64),
@@ -385,8 +397,9 @@ class PortScene:
                                else np.zeros(0, np.uint32)))
 
     def render(self, cam16, fov, width, height, spp, variant=0, gamma=True, y_begin=0, y_end=None,
-               want_hits=False, want_tuv=False, n_threads=0):
-        """-> dict(bgra [rows,W], tri [rows,W,spp]?, t/u/v?, counters)"""
+               want_hits=False, want_tuv=False, n_threads=0, ortho_width=None, shade_mode=0):
+        """-> dict(bgra [rows,W], tri [rows,W,spp]?, t/u/v?, counters).  ortho_width: orthographic camera
+        (camera.h:25-36); shade_mode 1 / 2: face normal / depth (renderer.cpp:116,118)"""
         y_end = height if y_end is None else y_end
         cam16 = np.ascontiguousarray(cam16, np.float32)
         rows = y_end - y_begin
@@ -396,10 +409,16 @@ class PortScene:
         u = np.empty((rows, width, spp), np.float32) if want_tuv else None
         v = np.empty((rows, width, spp), np.float32) if want_tuv else None
         cnt = Counters()
-        self.lib.rto_render_rows(C.byref(self.s), _p(cam16, _F32P), fov, width, height, spp, variant,
-                                 int(gamma), y_begin, y_end, n_threads or self.n_threads,
-                                 _p(bgra, _U32P), _p(tri, _U32P), _p(t, _F32P), _p(u, _F32P),
-                                 _p(v, _F32P), C.byref(cnt))
+        opt = _RenderOptions(int(ortho_width is not None), float(ortho_width or 0.0), int(shade_mode))
+        self.lib.rto_render_rows_ex.restype = None
+        self.lib.rto_render_rows_ex.argtypes = [C.POINTER(_Scene), _F32P, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                C.POINTER(_RenderOptions), _U32P, _U32P, _F32P, _F32P, _F32P,
+                                                C.POINTER(Counters)]
+        self.lib.rto_render_rows_ex(C.byref(self.s), _p(cam16, _F32P), fov, width, height, spp, variant,
+                                    int(gamma), y_begin, y_end, n_threads or self.n_threads, C.byref(opt),
+                                    _p(bgra, _U32P), _p(tri, _U32P), _p(t, _F32P), _p(u, _F32P),
+                                    _p(v, _F32P), C.byref(cnt))
         return dict(bgra=bgra, tri=tri, t=t, u=u, v=v, counters=cnt.as_dict())
 
     def intersect_rays(self, origins, dirs, variant=0):

@@ -431,6 +431,27 @@ void ref_generate_rays(void *h, uint32 width, uint32 height, uint32 spp, uint32 
             }
 }
 
+// The same through the orthographic branch of GenerateRay (camera.h:25-36), which RenderTile never takes
+void ref_generate_rays_ortho(void *h, uint32 width, uint32 height, uint32 spp, uint32 y_begin, uint32 y_end,
+                             float ortho_width, float *origins, float *dirs)
+{
+    RefRenderer *rr = static_cast<RefRenderer *>(h);
+    Matrix44f cam_mat;
+    float fov;
+    rr->scene->GetCameraParameters(fov, cam_mat);
+    std::vector<Vec2f> smp_loc;
+    SampleTable(spp, smp_loc);
+    for (uint y = y_begin; y < y_end; y++)
+        for (uint x = 0; x < width; x++)
+            for (uint smp = 0; smp < spp; smp++)
+            {
+                Vec3f origin, dir;
+                GenerateRay(cam_mat, Vec2ui(x, y), width, height, smp_loc[smp], true, ortho_width, origin, dir);
+                const size_t o = ((size_t(y - y_begin) * width + x) * spp + smp) * 3;
+                for (int i = 0; i < 3; i++) { origins[o + i] = origin[i]; dirs[o + i] = dir[i]; }
+            }
+}
+
 void ref_sample_table(uint32 spp, float *xy)
 {
     std::vector<Vec2f> smp_loc;

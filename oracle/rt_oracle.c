@@ -116,6 +116,24 @@ void rto_generate_ray(const float *m, uint32_t px, uint32_t py, uint32_t width, 
     dir[2] = n[0] * m[2] + n[1] * m[6] + n[2] * m[10];
 }
 
+/* camera.h:25-36: origin = Transf4x4((ndc.x * w/2, ndc.y * h/2, 0)), dir = Transf3x3((0, 0, -1)), every
+ * product and sum of lin_alg.h:495-535 spelled out (a zero factor still yields -0 / NaN where IEEE says so) */
+void rto_generate_ray_ortho(const float *m, uint32_t px, uint32_t py, uint32_t width, uint32_t height,
+                            float off_x, float off_y, float ortho_width, float aspect, float *origin, float *dir)
+{
+    const float ndc_x = (px + off_x) / (float) width * 2.0f - 1.0f;
+    const float ndc_y = (py + off_y) / (float) height * 2.0f - 1.0f;
+    const float w = ortho_width;
+    const float h = (float) w / aspect;
+    const float p[3] = { (float) (ndc_x * ((float) w / 2.0)), (float) (ndc_y * ((float) h / 2.0)), (float) 0.0 };
+    const float f[3] = { 0.0f, 0.0f, -1.0f };
+    for (int j = 0; j < 3; j++)
+    {
+        origin[j] = p[0] * m[0 + j] + p[1] * m[4 + j] + p[2] * m[8 + j] + m[12 + j];
+        dir[j] = f[0] * m[0 + j] + f[1] * m[4 + j] + f[2] * m[8 + j];
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * a4 -- box tests
  * ---------------------------------------------------------------------------------------- */
@@ -680,6 +698,7 @@ typedef struct render_job
     float fov_xs, aspect;
     uint32_t width, height, spp, y_begin, y_end;
     int variant, gamma;
+    rto_render_options opt;
     uint32_t *next_row;
     uint32_t *bgra, *hit_tri;
     float *hit_t, *hit_u, *hit_v;
@@ -701,10 +720,23 @@ static void *render_worker(void *arg)
             {
                 float o[3], d[3], t = 0, u = 0, v = 0, rgb[3];
                 uint32_t idx = RTO_MISS;
-                rto_generate_ray(j->cam16, x, y, j->width, j->height, j->smp[2 * s], j->smp[2 * s + 1],
-                                 j->fov_xs, j->aspect, o, d);
+                if (j->opt.ortho)
+                    rto_generate_ray_ortho(j->cam16, x, y, j->width, j->height, j->smp[2 * s], j->smp[2 * s + 1],
+                                           j->opt.ortho_width, j->aspect, o, d);
+                else
+                    rto_generate_ray(j->cam16, x, y, j->width, j->height, j->smp[2 * s], j->smp[2 * s + 1],
+                                     j->fov_xs, j->aspect, o, d);
                 const int hit = rto_grid_intersect(j->scene, o, d, j->variant, &t, &u, &v, &idx, &j->cnt);
-                if (hit)
+                if (hit && j->opt.shade_mode == RTO_SHADE_FACE_NORMAL)
+                {
+                    /* renderer.cpp:116 "Vec3f n = tri.n;" then :117 */
+                    const float *n = (const float *) (j->scene->tri + (size_t) idx * 6 + 3);
+                    for (int k = 0; k < 3; k++)
+                        rgb[k] = (n[k] + 1.0f) * 0.5f;
+                }
+                else if (hit && j->opt.shade_mode == RTO_SHADE_DEPTH)
+                    rgb[0] = rgb[1] = rgb[2] = t / 3; /* renderer.cpp:118 "col += Vec3f(t / 3);" */
+                else if (hit)
                     rto_shade_hit(j->scene, idx, u, v, rgb);
                 else
                     rgb[0] = rgb[1] = rgb[2] = (float) y / (float) j->height; /* renderer.cpp:121 */
@@ -727,6 +759,15 @@ void rto_render_rows(const rto_scene *scene, const float *cam16, float fov_deg, 
                      uint32_t y_end, uint32_t n_threads, uint32_t *bgra, uint32_t *hit_tri,
                      float *hit_t, float *hit_u, float *hit_v, rto_counters *cnt)
 {
+    rto_render_rows_ex(scene, cam16, fov_deg, width, height, spp, variant, gamma, y_begin, y_end, n_threads, NULL, bgra,
+                       hit_tri, hit_t, hit_u, hit_v, cnt);
+}
+
+void rto_render_rows_ex(const rto_scene *scene, const float *cam16, float fov_deg, uint32_t width,
+                        uint32_t height, uint32_t spp, int variant, int gamma, uint32_t y_begin,
+                        uint32_t y_end, uint32_t n_threads, const rto_render_options *opt, uint32_t *bgra,
+                        uint32_t *hit_tri, float *hit_t, float *hit_u, float *hit_v, rto_counters *cnt)
+{
     float *smp = (float *) malloc(sizeof(float) * 2 * (spp ? spp : 1));
     float fov_xs, aspect;
     uint32_t next_row = y_begin;
@@ -741,6 +782,7 @@ void rto_render_rows(const rto_scene *scene, const float *cam16, float fov_deg, 
         j->scene = scene; j->cam16 = cam16; j->smp = smp; j->fov_xs = fov_xs; j->aspect = aspect;
         j->width = width; j->height = height; j->spp = spp; j->y_begin = y_begin; j->y_end = y_end;
         j->variant = variant; j->gamma = gamma; j->next_row = &next_row;
+        if (opt) j->opt = *opt;
         j->bgra = bgra; j->hit_tri = hit_tri; j->hit_t = hit_t; j->hit_u = hit_u; j->hit_v = hit_v;
         pthread_create(&th[i], NULL, render_worker, j);
     }

@@ -72,6 +72,12 @@ void rto_camera_constants(float fov_deg, uint32_t width, uint32_t height, float 
 void rto_generate_ray(const float *cam16, uint32_t px, uint32_t py, uint32_t width, uint32_t height,
                       float off_x, float off_y, float fov_xs, float aspect, float *origin, float *dir);
 
+/* camera.h:25-36, the orthographic branch (never taken by RenderTile, which passes ortho = false).  The
+ * reference forms ndc * (float(width) / 2.0) in double and narrows it to float: the product of two floats is
+ * exact in double, so this is the correctly rounded float product */
+void rto_generate_ray_ortho(const float *cam16, uint32_t px, uint32_t py, uint32_t width, uint32_t height,
+                            float off_x, float off_y, float ortho_width, float aspect, float *origin, float *dir);
+
 /* a4: aabb.h:9-13 and aabb.h:34-83 */
 int rto_point_in_aabb(const float *p, const float *mn, const float *mx);
 int rto_ray_aabb(const float *o, const float *d, const float *mn, const float *mx, float *tmin, float *tmax);
@@ -104,6 +110,21 @@ void rto_render_rows(const rto_scene *scene, const float *cam16, float fov_deg, 
                      uint32_t height, uint32_t spp, int variant, int gamma, uint32_t y_begin,
                      uint32_t y_end, uint32_t n_threads, uint32_t *bgra, uint32_t *hit_tri,
                      float *hit_t, float *hit_u, float *hit_v, rto_counters *cnt);
+
+/* The alternates the reference keeps next to its live lines: the orthographic camera (camera.h:25-36) and
+ * the two commented-out shading lines of the pixel loop, "Vec3f n = tri.n" (renderer.cpp:116) and
+ * "col += Vec3f(t / 3)" (renderer.cpp:118) */
+enum { RTO_SHADE_NORMAL = 0 /* interpolated vertex normal (live) */, RTO_SHADE_FACE_NORMAL = 1, RTO_SHADE_DEPTH = 2 };
+typedef struct rto_render_options
+{
+    int   ortho;        /* 1: orthographic camera of width ortho_width (fov_deg ignored) */
+    float ortho_width;
+    int   shade_mode;   /* RTO_SHADE_* */
+} rto_render_options;
+void rto_render_rows_ex(const rto_scene *scene, const float *cam16, float fov_deg, uint32_t width,
+                        uint32_t height, uint32_t spp, int variant, int gamma, uint32_t y_begin,
+                        uint32_t y_end, uint32_t n_threads, const rto_render_options *opt, uint32_t *bgra,
+                        uint32_t *hit_tri, float *hit_t, float *hit_u, float *hit_v, rto_counters *cnt);
 
 void rto_intersect_rays(const rto_scene *scene, uint32_t n, const float *origins, const float *dirs,
                         int variant, uint32_t *tri_idx, float *t, float *u, float *v);

@@ -88,6 +88,22 @@ def test_grid_intersect_and_ray_march_single_ray(ref):
     assert hits > 5
 
 
+def test_renderer_alternates_match_port(port):
+    """Renderer::SetOrthographicWidth / SetShadingMode through the C++ mirror == the port's restatement of
+    camera.h:25-36 and renderer.cpp:116,118 (itself pinned to the reference on the CPU)."""
+    hostapi, scenes = pkg("hostapi"), pkg("scenes")
+    m, fov, cam = scenes.build(hostapi.host_api(), "cornell")
+    vtx, tri = m.arrays()
+    ps = port.scene(vtx, tri, 64)
+    hr = hostapi.HostRenderer(m, fov, cam)
+    w, h, spp = 150, 90, 4
+    for ortho, mode in ((1.6, 0), (0.0, 1), (0.0, 2), (1.2, 2), (0.0, 0)):
+        hr.set_alternates(ortho, mode)
+        _, img = hr.render(w, h, spp)
+        want = ps.render(cam, fov, w, h, spp, ortho_width=ortho if ortho else None, shade_mode=mode)["bgra"]
+        assert np.array_equal(img, want), (ortho, mode)
+
+
 def test_grid_info_matches_reference(ref):
     for name, res in (("killeroo", 64), ("room", 32)):
         hr, _, _ = _host_renderer(name, res)

@@ -238,6 +238,44 @@ def test_origin_relative_records(port, scene_data, monkeypatch, mode, name, spp)
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+@pytest.mark.parametrize("name,ortho_width", [("cornell", 1.7), ("killeroo", 1.3), ("room", 0.9)])
+def test_orthographic_camera(cuda_trace, port, scene_data, name, ortho_width):
+    """GenerateRay's orthographic branch (camera.h:25-36): every ray has its own origin.  Oracle = the port, whose
+    ortho rays and hits are pinned to the reference's GenerateRay(ortho = true) + Grid::Intersect on the CPU
+    (tests/test_oracle_vs_ref.py)."""
+    sd = scene_data(name)
+    w, h, spp = 160, 96, 4
+    cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
+    fov_xs, aspect = port.camera_constants(sd.fov, w, h)
+    f = cuda_trace.make_frame(w, h, spp, sd.cam16, fov_xs, aspect, keep_hits=True, ortho_width=ortho_width)
+    img = cuda_trace.trace_tiles(f)
+    tri, t, u, v = cuda_trace.download_hits(w, h, spp)
+    o = port.scene(sd.vtx, sd.tri, 64).render(sd.cam16, sd.fov, w, h, spp, want_hits=True, want_tuv=True,
+                                               ortho_width=ortho_width)
+    assert np.array_equal(tri, o["tri"]) and np.array_equal(img, o["bgra"])
+    for got, key in ((t, "t"), (u, "u"), (v, "v")):
+        assert np.array_equal(got.view(np.uint32), o[key].view(np.uint32))
+    assert (tri != 0xFFFFFFFF).sum() > 1000
+    plain = cuda_trace.trace_tiles(cuda_trace.make_frame(w, h, spp, sd.cam16, fov_xs, aspect, ortho_width=ortho_width))
+    assert np.array_equal(plain, img)
+
+
+@pytest.mark.parametrize("shade_mode", [1, 2])
+@pytest.mark.parametrize("name,spp", [("cornell", 1), ("head", 4), ("killeroo", 16)])
+def test_shading_alternates(cuda_trace, port, scene_data, name, spp, shade_mode):
+    """Face-normal and depth shading (renderer.cpp:116,118, commented out in the reference)."""
+    sd = scene_data(name)
+    w, h = 144, 100
+    cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
+    fov_xs, aspect = port.camera_constants(sd.fov, w, h)
+    img = cuda_trace.trace_tiles(cuda_trace.make_frame(w, h, spp, sd.cam16, fov_xs, aspect, shade_mode=shade_mode))
+    o = port.scene(sd.vtx, sd.tri, 64).render(sd.cam16, sd.fov, w, h, spp, shade_mode=shade_mode)
+    assert np.array_equal(img, o["bgra"])
+    if name != "cornell" or shade_mode == 2:  # the Cornell box is flat-shaded: its face normals ARE its vertex normals
+        live = cuda_trace.trace_tiles(cuda_trace.make_frame(w, h, spp, sd.cam16, fov_xs, aspect))
+        assert not np.array_equal(img, live)
+
+
 def test_brute_force_self_check(cuda_trace, ref, port, scene_data):
     """Renderer::IntersectBruteForce on the device: bit-exact against the reference's own brute force, and
     -- the author's cross-check -- equal to the grid result except where the grid's in-cell rule decides."""

@@ -118,6 +118,67 @@ def test_primary_rays_match_reference(port, ref):
                 assert np.array_equal(bits(o), bits(ro[y - 10, x, s])) and np.array_equal(bits(d), bits(rd[y - 10, x, s]))
 
 
+def test_orthographic_rays_and_frame_match_reference(port, ref):
+    """camera.h:25-36: the orthographic branch.  RenderTile never takes it, so the reference side is GenerateRay
+    called with ortho = true, then Grid::Intersect on those rays; the port's whole ortho frame must carry the same
+    per-sample hits."""
+    import ctypes as C
+    scenes = pkg("scenes")
+    for name, width_ortho in (("cornell", 1.7), ("killeroo", 1.3)):
+        m, fov, cam = scenes.build(ref.api, name)
+        r = ref.renderer(m, fov, cam)
+        w, h, spp = 61, 37, 3
+        ro, rd = r.generate_rays_ortho(w, h, spp, 0, h, width_ortho)
+        smp = port.sample_table(spp)
+        _, aspect = port.camera_constants(fov, w, h)
+        cam32 = np.ascontiguousarray(cam, np.float32)
+        F = C.POINTER(C.c_float)
+        port.lib.rto_generate_ray_ortho.argtypes = [F, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
+                                                    C.c_float, C.c_float, F, F]
+        for y in (0, 5, 36):
+            for x in (0, 1, 30, 60):
+                for k in range(spp):
+                    o, d = np.zeros(3, np.float32), np.zeros(3, np.float32)
+                    port.lib.rto_generate_ray_ortho(cam32.ctypes.data_as(F), x, y, w, h, float(smp[k, 0]), float(smp[k, 1]),
+                                                    width_ortho, float(aspect), o.ctypes.data_as(F), d.ctypes.data_as(F))
+                    assert np.array_equal(bits(o), bits(ro[y, x, k])) and np.array_equal(bits(d), bits(rd[y, x, k]))
+        idx, t, u, v = r.intersect_rays(ro, rd)
+        vtx, tri = r.mesh_arrays()
+        o = port.scene(vtx, tri, 64).render(cam, fov, w, h, spp, want_hits=True, want_tuv=True, ortho_width=width_ortho)
+        assert np.array_equal(o["tri"].ravel(), idx) and (idx != 0xFFFFFFFF).sum() > 500
+        for got, want in ((o["t"], t), (o["u"], u), (o["v"], v)):
+            assert np.array_equal(bits(got.ravel()), bits(want))
+
+
+def test_shading_alternates_restate_the_commented_lines(port, ref):
+    """renderer.cpp:116 "Vec3f n = tri.n" and :118 "col += Vec3f(t / 3)" have no call site to run; the port's two
+    extra shading modes are checked against those expressions evaluated on the reference's own hits."""
+    scenes = pkg("scenes")
+    m, fov, cam = scenes.build(ref.api, "cornell")
+    r = ref.renderer(m, fov, cam)
+    w, h = 48, 40
+    idx, t, u, v = r.trace_hits(w, h, 1)
+    vtx, tri = r.mesh_arrays()
+    ps = port.scene(vtx, tri, 64)
+    hit = idx[:, :, 0] != 0xFFFFFFFF
+    miss_grey = (np.arange(h, dtype=np.float32) / np.float32(h))[:, None] * np.ones((1, w), np.float32)
+
+    def pack(rgb):  # lin_alg.h:125-132 after renderer.cpp:124-131 with one sample
+        c = np.sqrt(rgb.astype(np.float64)).astype(np.float32)  # powf(x, .5f): never a different byte (exhaustive scan)
+        b = np.where(c > 1.0, 255, (c * np.float32(255.0)).astype(np.int64) & 0xFF).astype(np.uint32)
+        return (b[..., 0] << 16) | (b[..., 1] << 8) | b[..., 2]
+
+    face = tri[:, 3:6].copy().view(np.float32)[np.where(hit, idx[:, :, 0], 0)]
+    want_face = np.where(hit[..., None], (face + np.float32(1.0)) * np.float32(0.5), miss_grey[..., None])
+    got_face = ps.render(cam, fov, w, h, 1, shade_mode=1)["bgra"]
+    assert np.array_equal(got_face, pack(want_face))
+    depth = (t[:, :, 0] / np.float32(3))[..., None] * np.ones(3, np.float32)
+    want_depth = np.where(hit[..., None], depth, miss_grey[..., None])
+    got_depth = ps.render(cam, fov, w, h, 1, shade_mode=2)["bgra"]
+    assert np.array_equal(got_depth, pack(want_depth))
+    assert not np.array_equal(got_face, got_depth)
+
+
 def test_arbitrary_rays_match_reference(port, ref):
     scenes = pkg("scenes")
     m, fov, cam = scenes.build(ref.api, "cornell")
