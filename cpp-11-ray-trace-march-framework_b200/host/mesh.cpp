@@ -6,6 +6,7 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <string>
 
@@ -51,11 +52,80 @@ struct Tokens
         skip_space();
         return p >= end;
     }
+    // "%f" semantics = strtof.  Plain decimals take a fast exact path (Clinger): up to 2^53 as an integer
+    // mantissa times / over a power of ten <= 10^22 is a correctly rounded double, and narrowing that to float
+    // rounds like the decimal itself unless the double sits exactly on a float rounding midpoint (then, and for
+    // anything unusual -- inf, nan, hex floats, subnormal or huge values, very long mantissas -- strtof decides)
     bool next_float(float& out)
     {
+        static const double kPow10[23] = { 1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                           1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22 };
         skip_space();
         if (p >= end)
             return false;
+        const char *s = p;
+        bool neg = false;
+        if (s < end && (*s == '-' || *s == '+'))
+            neg = *s++ == '-';
+        unsigned long long mant = 0;
+        int digits = 0, exp10 = 0;
+        bool any = false, fast = true;
+        for (; s < end && *s >= '0' && *s <= '9'; s++, any = true)
+        {
+            if (mant || *s != '0')
+                digits++;
+            if (digits <= 18)
+                mant = mant * 10 + (unsigned) (*s - '0');
+            else
+                fast = false;
+        }
+        if (s < end && *s == '.')
+        {
+            s++;
+            for (; s < end && *s >= '0' && *s <= '9'; s++, any = true)
+            {
+                if (mant || *s != '0')
+                    digits++;
+                if (digits <= 18)
+                {
+                    mant = mant * 10 + (unsigned) (*s - '0');
+                    exp10--;
+                }
+                else
+                    fast = false;
+            }
+        }
+        if (any && fast && s < end && (*s == 'e' || *s == 'E'))
+        {
+            const char *e = s + 1;
+            bool eneg = false;
+            if (e < end && (*e == '-' || *e == '+'))
+                eneg = *e++ == '-';
+            if (e < end && *e >= '0' && *e <= '9')
+            {
+                int ev = 0;
+                for (; e < end && *e >= '0' && *e <= '9'; e++)
+                    ev = ev < 10000 ? ev * 10 + (*e - '0') : ev;
+                exp10 += eneg ? -ev : ev;
+                s = e;
+            }
+        }
+        // what follows must end the number the way strtof would see it (hex floats, "inf", "nan" start differently)
+        const bool plain_end = s >= end || *s == ' ' || *s == '\t' || *s == '\r' || *s == '\n' || *s == '\f' || *s == '\v';
+        if (any && fast && plain_end && mant < (1ull << 53) && exp10 >= -22 && exp10 <= 22)
+        {
+            const double v = exp10 < 0 ? (double) mant / kPow10[-exp10] : (double) mant * kPow10[exp10];
+            unsigned long long bits;
+            std::memcpy(&bits, &v, sizeof(bits));
+            const bool on_midpoint = (bits & 0x1FFFFFFFull) == 0x10000000ull;
+            if (!on_midpoint && (v == 0.0 || (v > 1.2e-38 && v < 3.4e38)))
+            {
+                const float f = (float) v;
+                out = neg ? -f : f;
+                p = s;
+                return true;
+            }
+        }
         char *stop = nullptr;
         out = std::strtof(p, &stop);
         if (stop == p)

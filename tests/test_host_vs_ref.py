@@ -97,6 +97,35 @@ def test_ascii_reader_matches_reference_and_assets(host, ref):
             assert np.array_equal(at, rt) and np.array_equal(av.view(np.uint32), rv.view(np.uint32)), name
 
 
+def test_float_parsing_matches_reference_on_hard_decimals(host, ref, tmp_path):
+    """The host reader parses plain decimals on a fast exact path and leaves the rest to strtof (host/mesh.cpp);
+    the reference uses fscanf("%f").  Positions written in every notation that occurs in practice plus the hard
+    cases: float rounding midpoints spelled out exactly, one digit above / below them, 17+ significant digits,
+    exponents, subnormals, signed zeros, huge values.  Non-indexed position-only mesh: three floats per line."""
+    rs = np.random.RandomState(11)
+    vals = []
+    f32 = rs.standard_normal(600).astype(np.float32) * np.float32(10.0) ** rs.randint(-6, 7, 600).astype(np.float32)
+    for x in f32:
+        lo, hi = float(x), float(np.nextafter(x, np.float32(np.inf)))
+        mid = (lo + hi) / 2                                   # exactly representable in double
+        vals += ["%.6f" % lo, "%.9g" % lo, "%.17g" % lo, "%.30f" % mid, "%.25e" % mid,
+                 "%.17g" % np.nextafter(mid, np.inf), "%.17g" % np.nextafter(mid, -np.inf)]
+    vals += ["0", "-0", "0.0", "-0.000", "1e-45", "1.4e-45", "7e-46", "1e-40", "-3.4028235e38", "3.4028234e+38",
+             "1e22", "1e23", "123456789012345678", "1234567890123456789012", "0.1", ".5", "5.", "+2.5", "1E3", "1e+3",
+             "100000000000000000000e-20", "0.000000000000000000001e21", "9007199254740993", "16777217", "33554433"]
+    while len(vals) % 9:
+        vals.append("1")
+    lines = [" ".join(vals[i:i + 3]) for i in range(0, len(vals), 3)]
+    path = tmp_path / "hard.dat"
+    path.write_text("\n".join(lines) + "\n")
+    hm, rm = host.mesh(), ref.api.mesh()
+    assert hm.read_file(str(path)) and rm.read_file(str(path))
+    hv, _ = hm.arrays()
+    rv, _ = rm.arrays()
+    assert len(hv) == len(vals) // 3
+    assert np.array_equal(hv[:, :3].view(np.uint32), rv[:, :3].view(np.uint32))
+
+
 def test_reader_errors(host, tmp_path):
     m = host.mesh()
     assert not m.read_file(str(tmp_path / "missing.dat"))
