@@ -355,6 +355,17 @@ def run_ours(args, wl, rank, world, local_rank, dist):
                      "frac": alg_flops / sec / 1e12 / fp32_peak, "algorithmic_flops_per_launch": alg_flops},
             "counters": counters,
         }
+        try:
+            # ceilings measured on this box right now (csrc/peaks.cu): FP32 without FMA, L2 read bandwidth
+            fp32_meas, l2_meas = capi.measure_peaks(local_rank)
+            line["roofline"]["fp32"].update({"peak_tflops_nonfma_measured": fp32_meas,
+                                             "frac_of_measured": alg_flops / sec / 1e12 / fp32_meas})
+            line["roofline"]["l2"] = {"achieved": alg_bytes / sec / 1e9, "peak_measured": l2_meas, "unit": "GB/s",
+                                      "frac": alg_bytes / sec / 1e9 / l2_meas,
+                                      "note": "algorithmic bytes against the measured L2 read bandwidth (SURVEY 8d: the "
+                                              "bandwidth roofline of the L2-resident configs)"}
+        except Exception as e:  # the figures above stand without it
+            line["roofline"]["fp32"]["peak_measured_error"] = str(e)
     if world == 1 and not args.no_cpu_baseline:
         base = time_reference_cpu(wl, 1, 0, budget_s=25.0)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}

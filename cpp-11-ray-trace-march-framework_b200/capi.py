@@ -68,6 +68,7 @@ SYMBOLS = {
     "cuda_trace_intersect_rays": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, C.c_uint32, _U32P, _F32P,
                                             _F32P, _F32P]),
     "cuda_trace_intersect_rays_brute_force": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P, _F32P, _F32P]),
+    "cuda_trace_measure_peaks": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cuda_trace_last_call_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "cuda_trace_download_strip_cycles": (C.c_int, [C.c_void_p, _U32P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "cuda_trace_ray_march": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P]),
@@ -130,6 +131,16 @@ def full_frame_tiles(width, height, tiles_x=12, tiles_y=9):
             out.append((x * tw, y * th, width if x == tiles_x - 1 else (x + 1) * tw,
                         height if y == tiles_y - 1 else (y + 1) * th))
     return out
+
+
+def measure_peaks(device=0):
+    """-> (FP32 non-FMA T instr-flop/s, L2 read GB/s) measured on ``device`` (csrc/peaks.cu)."""
+    lib = load_library()
+    a, b = C.c_double(), C.c_double()
+    rc = lib.cuda_trace_measure_peaks(device, C.byref(a), C.byref(b))
+    if rc:
+        raise RuntimeError("cuda_trace_measure_peaks failed: %d" % rc)
+    return a.value, b.value
 
 
 class PinnedImage:

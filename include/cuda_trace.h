@@ -216,6 +216,11 @@ int cuda_trace_qmc_cranley_patterson(cuda_trace_ctx *ctx, const double *x, doubl
 int cuda_trace_set_counting(cuda_trace_ctx *ctx, int enable);
 int cuda_trace_get_counters(cuda_trace_ctx *ctx, cuda_trace_counters *out);
 
+/* Measured ceilings for the roofline figures: FP32 throughput without fused multiply-add (the
+ * kernels are built -fmad=false) in T instr-flop/s, and L2 read bandwidth on an L2-resident buffer in GB/s.
+ * A micro-benchmark (~0.2 s); no context needed. */
+int cuda_trace_measure_peaks(int device, double *fp32_nonfma_tflops, double *l2_read_gbps);
+
 /* Host-clock marks of the last cuda_trace_tiles call, in ms since its entry: [0] work submitted, [1] trace stream
  * drained, [2] read-back copies drained (overlapped mode), [3] return, [4] host set-up done, [5] / [6] before /
  * after the launch of the first device's trace kernel.  Diagnostics for the end-to-end figure. */
