@@ -26,14 +26,21 @@ struct Mesh
     std::vector<Triangle> m_triangles;
     std::vector<Vertex>   m_vertices;
 
-    void Clear();
-    void ComputeAABB(Vec3f& aabb_min, Vec3f& aabb_max) const;
-    void Transform(Matrix44f mat);
-    void AddQuad(const float *quad_vtx); // 4 x 3 floats
-    void AddMesh(const Mesh& mesh);
-    void NormalizeDimensions();
+    // -- sources: an ASCII .dat file (position / +normal / +uv per line, indexed or not; false + a Trace line on
+    //    failure), the built-in Cornell box (16 quads), or nothing
     bool Read(const char *filename, bool flip_winding = false);
     void CornellBox();
+    void Clear();
+
+    // -- composition: one quad as two triangles (4 x 3 floats, flat normal), or all of another mesh
+    void AddQuad(const float *quad_vtx);
+    void AddMesh(const Mesh& mesh);
+
+    // -- geometry: bounds over the referenced vertices, row-vector transform of positions and normals, and
+    //    "centre at the origin, longest side = 1"
+    void ComputeAABB(Vec3f& aabb_min, Vec3f& aabb_max) const;
+    void Transform(Matrix44f mat);
+    void NormalizeDimensions();
 
     // Additions (not in the reference): the binary asset format of oracle/convert_meshes.py --
     // the state of a Mesh right after Read() -- and direct array access for the C wrappers
