@@ -68,6 +68,8 @@ SYMBOLS = {
     "cuda_trace_intersect_rays": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, C.c_uint32, _U32P, _F32P,
                                             _F32P, _F32P]),
     "cuda_trace_intersect_rays_brute_force": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P, _F32P, _F32P]),
+    "cuda_trace_band_shares": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         _U32P, _U32P, _U32P, _U32P, _U32P]),
     "cuda_trace_measure_peaks": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cuda_trace_last_call_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "cuda_trace_download_strip_cycles": (C.c_int, [C.c_void_p, _U32P, C.c_uint64, C.POINTER(C.c_uint64)]),
@@ -131,6 +133,20 @@ def full_frame_tiles(width, height, tiles_x=12, tiles_y=9):
             out.append((x * tw, y * th, width if x == tiles_x - 1 else (x + 1) * tw,
                         height if y == tiles_y - 1 else (y + 1) * th))
     return out
+
+
+def band_shares(width, height, spp, rects, world, chunk=32):
+    """Host arithmetic of the overlapped read-back (no device needed): -> dict(shares [world, 32], gpus_in_band [32],
+    band_rows, n_bands, pieces_per_strip) for the frame layout ``rects``."""
+    lib = load_library()
+    tiles, n_tiles = CudaTrace.make_tiles(rects)
+    shares, gpus = np.zeros((world, 32), np.uint32), np.zeros(32, np.uint32)
+    rows, nb, pieces = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = lib.cuda_trace_band_shares(width, height, spp, tiles, n_tiles, world, chunk, _p(shares, _U32P), _p(gpus, _U32P),
+                                    C.byref(rows), C.byref(nb), C.byref(pieces))
+    if rc:
+        raise ValueError("cuda_trace_band_shares: bad arguments")
+    return dict(shares=shares, gpus_in_band=gpus, band_rows=rows.value, n_bands=nb.value, pieces_per_strip=pieces.value)
 
 
 def measure_peaks(device=0):

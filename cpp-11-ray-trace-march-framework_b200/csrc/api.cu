@@ -276,6 +276,17 @@ double ms_since(std::chrono::steady_clock::time_point t0)
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// Row bands of the overlapped read-back: ~1 MB of pixels per band (a DMA that size runs at full PCIe rate; the
+// last band's copy is the exposed tail), at most kMaxBands; a small frame is one band -- one wait and one copy
+// instead of dozens of driver calls.  A band is never lower than a strip.
+void band_layout(uint32_t width, uint32_t height, uint32_t strip_h, uint32_t& band_rows, uint32_t& n_bands)
+{
+    const uint64_t frame_bytes = (uint64_t) width * height * sizeof(uint32_t);
+    const uint32_t want_bands = (uint32_t) std::min<uint64_t>(kMaxBands, std::max<uint64_t>(1, frame_bytes >> 20));
+    band_rows = std::max<uint32_t>(strip_h, (height + want_bands - 1) / want_bands);
+    n_bands = (height + band_rows - 1) / band_rows;
+}
+
 // Pieces of strips per row band for every participating GPU (`world` of them; strips dealt in chunks of
 // `chunk`, owner rotating from round to round -- the same arithmetic as in trace_tiles_kernel), and how many GPUs
 // have a share in each band.  A strip that straddles a band boundary counts in both, exactly as the kernel
@@ -786,12 +797,7 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
     const bool use_bands = ctx->shard_signals || can_overlap || std::getenv("RTM_FORCE_BANDS") != nullptr;
     if (use_bands)
     {
-        // ~1 MB per band (a DMA that size runs at full PCIe rate; the last band's copy is the exposed tail), at
-        // most kMaxBands; a small frame is one band -- one wait and one copy instead of dozens of driver calls
-        const uint64_t frame_bytes = (uint64_t) f->width * f->height * sizeof(uint32_t);
-        const uint32_t want_bands = (uint32_t) std::min<uint64_t>(kMaxBands, std::max<uint64_t>(1, frame_bytes >> 20));
-        ctx->band_rows = std::max<uint32_t>(strip_h, (f->height + want_bands - 1) / want_bands);
-        ctx->n_bands = (f->height + ctx->band_rows - 1) / ctx->band_rows;
+        band_layout(f->width, f->height, strip_h, ctx->band_rows, ctx->n_bands);
         const uint32_t participants = ctx->shard_world * (uint32_t) ctx->dev.size();
         // one GPU storing into its own framebuffer counts pieces straight into the band counters (a release at
         // GPU scope is cheap); several GPUs count locally first and bump the shared counter once per band
@@ -1508,6 +1514,37 @@ int cuda_trace_get_counters(cuda_trace_ctx *ctx, cuda_trace_counters *out)
         CK(cudaMemcpy(&c, d.d_counters, sizeof(c), cudaMemcpyDeviceToHost));
         out->rays += c.rays; out->cells += c.cells; out->tri_tests += c.tri_tests; out->hits += c.hits;
     }
+    return 0;
+}
+
+int cuda_trace_band_shares(uint32_t width, uint32_t height, uint32_t spp, const cuda_trace_tile_rect *tiles, uint32_t n_tiles,
+                           uint32_t world, uint32_t chunk, uint32_t *shares, uint32_t *gpus_in_band, uint32_t *band_rows,
+                           uint32_t *n_bands, uint32_t *pieces_per_strip)
+{
+    if (!tiles || !n_tiles || !world || !chunk || !shares || !gpus_in_band || !band_rows || !n_bands || !pieces_per_strip ||
+        !width || !height || !spp)
+        return CUDA_TRACE_ERR_ARG;
+    uint32_t strip_w, strip_h;
+    strip_size_for_spp(spp, (uint64_t) width * height * spp, strip_w, strip_h);
+    *pieces_per_strip = strip_split_parts(strip_w, strip_h, spp);
+    std::vector<uint4> rects(n_tiles);
+    std::vector<uint32_t> prefix(n_tiles + 1, 0);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_tiles; i++)
+    {
+        const cuda_trace_tile_rect& t = tiles[i];
+        if (t.x0 > t.x1 || t.y0 > t.y1 || t.x1 > width || t.y1 > height)
+            return CUDA_TRACE_ERR_ARG;
+        rects[i] = make_uint4(t.x0, t.y0, t.x1, t.y1);
+        prefix[i] = (uint32_t) total;
+        total += (uint64_t) ((t.x1 - t.x0 + strip_w - 1) / strip_w) * ((t.y1 - t.y0 + strip_h - 1) / strip_h);
+    }
+    prefix[n_tiles] = (uint32_t) total;
+    band_layout(width, height, strip_h, *band_rows, *n_bands);
+    std::vector<std::array<uint32_t, kMaxBands>> share;
+    band_shares(rects, prefix, strip_w, strip_h, *band_rows, *pieces_per_strip, chunk, world, share, gpus_in_band);
+    for (uint32_t q = 0; q < world; q++)
+        std::memcpy(shares + (size_t) q * kMaxBands, share[q].data(), sizeof(uint32_t) * kMaxBands);
     return 0;
 }
 

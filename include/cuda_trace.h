@@ -226,6 +226,15 @@ int cuda_trace_measure_peaks(int device, double *fp32_nonfma_tflops, double *l2_
  * after the launch of the first device's trace kernel.  Diagnostics for the end-to-end figure. */
 int cuda_trace_last_call_timing(cuda_trace_ctx *ctx, double ms[7]);
 
+/* Host arithmetic only (no device): the per-GPU completion targets of the overlapped read-back for a frame
+ * layout -- shares[q * 32 + b] = pieces of strips GPU q of `world` finishes in row band b (strips dealt in chunks
+ * of `chunk`), gpus_in_band[b] = GPUs with a share in band b, plus the band height / count and the pieces a strip
+ * counts as.  What cuda_trace_tiles programs into the kernel and waits for; exported for CPU tests of the
+ * multi-GPU bookkeeping. */
+int cuda_trace_band_shares(uint32_t width, uint32_t height, uint32_t spp, const cuda_trace_tile_rect *tiles, uint32_t n_tiles,
+                           uint32_t world, uint32_t chunk, uint32_t *shares, uint32_t *gpus_in_band, uint32_t *band_rows,
+                           uint32_t *n_bands, uint32_t *pieces_per_strip);
+
 /* Scheduler diagnostics: SM cycles each strip of the last frame took on device 0, in this shard's strip order
  * (the input of the cost-ordered scheduling, csrc/schedule.cu).  *count = strips recorded (0 when the last frame
  * ran without cost recording -- see RTM_COST_ORDER); at most `capacity` values are written. */

@@ -83,3 +83,37 @@ def test_gloo_world_size_2(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "rank0ok" in r.stdout and "rank1ok" in r.stdout
+
+
+@pytest.mark.parametrize("size,spp", [((3840, 2160), 16), ((1920, 1080), 4), ((512, 512), 1), ((333, 217), 2), ((640, 360), 64)])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_band_completion_targets_match_the_strip_partition(size, spp, world):
+    """What cuda_trace_tiles programs into the kernel and waits for (per-GPU pieces of strips per row band, host
+    arithmetic in csrc/api.cu) against the strip partition restated in multirank.py: every strip counts its pieces in
+    the band of its first and, when it straddles a boundary, of its last row, for the rank that owns it."""
+    capi, mr = pkg("capi"), pkg("multirank")
+    w, h = size
+    rects = capi.full_frame_tiles(w, h)
+    got = capi.band_shares(w, h, spp, rects, world)
+    rays = w * h * spp
+    sw, sh = mr.strip_size(spp, rays)
+    assert got["band_rows"] >= sh and got["n_bands"] == -(-h // got["band_rows"]) and 1 <= got["n_bands"] <= 32
+    assert got["pieces_per_strip"] in (1, 2, 4)
+    want = np.zeros((world, 32), np.int64)
+    prefix = mr.strip_prefix(rects, spp, rays)
+    for tile, (x0, y0, x1, y1) in enumerate(rects):
+        nx = -(-(x1 - x0) // sw)
+        for row, y in enumerate(range(y0, y1, sh)):
+            b0, b1 = y // got["band_rows"], (min(y + sh, y1) - 1) // got["band_rows"]
+            ids = prefix[tile] + row * nx + np.arange(nx)
+            owners = np.array([mr.strip_owner(int(s), world) for s in ids[:: max(1, mr.SHARD_CHUNK // 4)]])  # spot ...
+            c = ids // mr.SHARD_CHUNK
+            own = (c % world + c // world) % world                                                       # ... and all
+            assert np.array_equal(own[:: max(1, mr.SHARD_CHUNK // 4)], owners)
+            np.add.at(want[:, b0], own, got["pieces_per_strip"])
+            if b1 != b0:
+                np.add.at(want[:, b1], own, got["pieces_per_strip"])
+    assert np.array_equal(got["shares"].astype(np.int64), want)
+    assert np.array_equal(got["gpus_in_band"], (want > 0).sum(axis=0))
+    assert want[:, got["n_bands"]:].sum() == 0 and want.sum() >= prefix[-1] * got["pieces_per_strip"]
+
