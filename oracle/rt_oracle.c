@@ -544,6 +544,24 @@ static int to_voxel(const rto_grid *g, const float *p, int axis)
 static float to_pos(const rto_grid *g, int vox, int axis) { return g->aabb_min[axis] + vox * g->cell_wdh; }
 
 /* grid.cpp:159-281 */
+/* Walk recorder (scheduling studies only, tools/warp_walk_model.py): when armed, rto_grid_intersect appends the
+ * triangle-list length of every cell it visits, in order */
+static __thread uint16_t *g_walk_out;
+static __thread uint32_t g_walk_cap, g_walk_n;
+
+uint32_t rto_ray_walk_profile(const rto_scene *sc, const float *origin, const float *dir, uint32_t cap,
+                              uint16_t *list_lengths, int *hit)
+{
+    float t, u, v;
+    uint32_t idx;
+    g_walk_out = list_lengths;
+    g_walk_cap = cap;
+    g_walk_n = 0;
+    *hit = rto_grid_intersect(sc, origin, dir, RTO_VARIANT_MT, &t, &u, &v, &idx, NULL);
+    g_walk_out = NULL;
+    return g_walk_n;
+}
+
 int rto_grid_intersect(const rto_scene *sc, const float *origin, const float *dir, int variant,
                        float *t, float *u, float *v, uint32_t *tri_idx, rto_counters *cnt)
 {
@@ -607,6 +625,13 @@ int rto_grid_intersect(const rto_scene *sc, const float *origin, const float *di
                               (uint64_t) pos[1] * g->dim[0] * g->dim[2];
         if (cnt) cnt->cells++;
         if (cnt && g->cell_offset[cell] != g->cell_offset[cell + 1]) cnt->nonempty++;
+        if (g_walk_out)
+        {
+            const uint64_t len = g->cell_offset[cell + 1] - g->cell_offset[cell];
+            if (g_walk_n < g_walk_cap)
+                g_walk_out[g_walk_n] = (uint16_t) (len > 65535 ? 65535 : len);
+            g_walk_n++;
+        }
         for (uint64_t k = g->cell_offset[cell]; k < g->cell_offset[cell + 1]; k++)
         {
             const uint32_t ci = g->tri_index[k];

@@ -99,6 +99,12 @@ int  rto_tri_box_overlap(const double center[3], const double half[3], const dou
 int rto_grid_intersect(const rto_scene *scene, const float *origin, const float *dir, int variant,
                        float *t, float *u, float *v, uint32_t *tri_idx, rto_counters *cnt);
 
+/* Scheduling studies (tools/warp_walk_model.py): the triangle-list lengths of the cells a ray visits, in order
+ * (0 = empty cell); the last one is the cell of the hit when *hit.  Returns the number of cells visited (may
+ * exceed cap; only cap entries are written) */
+uint32_t rto_ray_walk_profile(const rto_scene *scene, const float *origin, const float *dir, uint32_t cap,
+                              uint16_t *list_lengths, int *hit);
+
 /* a7 + a8 helpers: renderer.cpp:107-121, triangle.h:158-161, renderer.cpp:124-133, lin_alg.h:125-132 */
 void     rto_shade_hit(const rto_scene *scene, uint32_t tri_idx, float u, float v, float *rgb);
 uint32_t rto_resolve_pixel(const float *rgb_sum, uint32_t spp, int gamma);
