@@ -46,6 +46,7 @@ static void cnt_add(rto_counters *dst, const rto_counters *src)
     dst->rej_v += src->rej_v;         dst->full += src->full;
     dst->box_miss += src->box_miss;
     dst->rep2 += src->rep2; dst->rep8 += src->rep8; dst->rep64 += src->rep64; dst->nonempty += src->nonempty;
+    dst->pre_reject += src->pre_reject; dst->pre_violation += src->pre_violation; dst->pre_keep_fail += src->pre_keep_fail;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -657,6 +658,29 @@ int rto_grid_intersect(const rto_scene *sc, const float *origin, const float *di
                 hit = rto_ray_tri_bary(origin, dir, v0, v1, v2, (const float *) (tr + 3), &ct, &cu, &cv, cnt);
             else
                 hit = rto_ray_tri(origin, dir, v0, v1, v2, &ct, &cu, &cv, cnt);
+            if (cnt && variant == RTO_VARIANT_MT)
+            {
+                /* pre-test study: |tvec x d|^2 > thresh, tvec = origin - v0, thresh = 1.01 * max(|e1|^2, |e2|^2)
+                 * + 32 ulp-scale * |tvec|^2 (the rounding error of the left side), all in fp32 without contraction */
+                const float tv[3] = { origin[0] - v0[0], origin[1] - v0[1], origin[2] - v0[2] };
+                const float e1[3] = { v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2] };
+                const float e2[3] = { v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2] };
+                const float l1 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2];
+                const float l2 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
+                const float tt = tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2];
+                const float thresh = (l1 > l2 ? l1 : l2) * 1.01f + tt * (32.0f * 5.9604645e-8f);
+                const float qx = tv[1] * dir[2] - tv[2] * dir[1];
+                const float qy = tv[2] * dir[0] - tv[0] * dir[2];
+                const float qz = tv[0] * dir[1] - tv[1] * dir[0];
+                const float s = qx * qx + qy * qy + qz * qz;
+                if (s > thresh)
+                {
+                    cnt->pre_reject++;
+                    if (hit) cnt->pre_violation++;
+                }
+                else if (!hit)
+                    cnt->pre_keep_fail++;
+            }
             if (hit && ct < *t && ct < next_t[sa])
             {
                 *t = ct; *u = cu; *v = cv; *tri_idx = ci;

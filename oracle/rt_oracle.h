@@ -59,6 +59,11 @@ typedef struct rto_counters
     uint64_t rep8;       /* ... among the last 8 distinct ids tested by this ray */
     uint64_t rep64;      /* ... among the last 64 */
     uint64_t nonempty;   /* visited cells with a non-empty list */
+    /* pre-test study: a conservative reject in front of the ray/triangle test -- the ray
+     * line's squared distance from v0 against (max edge length from v0)^2 with safety margins, in fp32 */
+    uint64_t pre_reject;      /* tests the pre-test would skip                                  */
+    uint64_t pre_violation;   /* ... of which the exact test reports a hit (must stay 0)        */
+    uint64_t pre_keep_fail;   /* tests the pre-test keeps and the exact test then rejects       */
 } rto_counters;
 
 enum { RTO_VARIANT_MT = 0 /* IntersectRayTri */, RTO_VARIANT_BARY = 1 /* IntersectRayTriBarycentric */ };
