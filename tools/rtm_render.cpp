@@ -3,7 +3,7 @@
 //
 //   rtm_render --scene killeroo|<file.dat|file.meshbin> [--width W] [--height H] [--spp N]
 //              [--grid-res R] [--variant 0|1] [--gpus G] [--frames F] [--eye x y z] [--at x y z]
-//              [--fov deg] [--out image.bmp]
+//              [--fov deg] [--ortho width] [--shade 0|1|2] [--out image.bmp]
 //
 // Built by <package>/build.py as <package>/rtm_render.
 #include <cstdio>
@@ -28,7 +28,8 @@ bool ends_with(const std::string& s, const char *suffix)
 int main(int argc, char **argv)
 {
     std::string scene = "cornell", out = "out.bmp", assets = "assets/meshes";
-    uint width = 1920, height = 1080, spp = 16, grid_res = 64, variant = 0, gpus = 1, frames = 1;
+    uint width = 1920, height = 1080, spp = 16, grid_res = 64, variant = 0, gpus = 1, frames = 1, shade = 0;
+    float ortho_width = 0.0f; // > 0: orthographic camera of that width (camera.h:25-36)
     float eye[3] = { -1.6f, 1.2f, -1.0f }, at[3] = { 0.0f, 0.0f, -0.1f }, fov = 30.0f;
     bool camera_given = false;
     for (int i = 1; i < argc; i++)
@@ -47,6 +48,8 @@ int main(int argc, char **argv)
         else if (a == "--fov") { fov = float(std::atof(next())); camera_given = true; }
         else if (a == "--eye") { for (float& v : eye) v = float(std::atof(next())); camera_given = true; }
         else if (a == "--at") { for (float& v : at) v = float(std::atof(next())); camera_given = true; }
+        else if (a == "--ortho") ortho_width = float(std::atof(next()));
+        else if (a == "--shade") shade = uint(std::atoi(next())); // 1 face normals, 2 depth (renderer.cpp:116,118)
         else if (a == "--out") out = next();
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -85,6 +88,8 @@ int main(int argc, char **argv)
         Renderer renderer(std::move(sc));
         renderer.SetSampleCount(spp);
         renderer.SetIntersectVariant(variant);
+        renderer.SetOrthographicWidth(ortho_width);
+        renderer.SetShadingMode(shade);
         for (uint f = 0; f < frames; f++)
         {
             if (f == 0)
