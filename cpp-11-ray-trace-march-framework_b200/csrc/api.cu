@@ -50,7 +50,9 @@ struct DeviceState
     uint32_t *d_cell_start = nullptr, *d_cell_occ = nullptr, *d_tri_index = nullptr;
     uint32_t *d_pcell_start = nullptr, *d_pcell_occ = nullptr; // padded grid (rt_device.cuh)
     float4 *d_cell_tris = nullptr, *d_cell_tris_b = nullptr, *d_tri_normals = nullptr;
-    float4 *d_cell_tris_rel = nullptr; // records relative to rel_origin (primary rays; built on demand, pack.cu)
+    uint32_t *d_ppair_start = nullptr;  // padded CSR of the pair records (rt_device.cuh)
+    float4 *d_pair_recs = nullptr;      // two triangles per record, interleaved: the packed-fp32 test of K1
+    float4 *d_pair_recs_rel = nullptr;  // ... relative to rel_origin (primary rays; built on demand, pack.cu)
     float rel_origin[3] = { 0.0f, 0.0f, 0.0f };
     bool rel_valid = false;
 
@@ -88,6 +90,7 @@ struct cuda_trace_ctx
     bool have_scene = false;
     cuda_trace_grid_desc desc;
     uint32_t num_vtx = 0, num_tri = 0;
+    uint32_t num_pairs = 0; // pair records (two cell references each, rt_device.cuh)
 
     uint32_t shard_rank = 0, shard_world = 1;
     uint32_t shard_chunk = 32; // consecutive strips dealt to one shard at a time (one CTA's worth of warps)
@@ -160,8 +163,8 @@ void free_scene(DeviceState& d)
     cudaSetDevice(d.ordinal);
     cudaFree(d.d_vtx); cudaFree(d.d_tri); cudaFree(d.d_cell_start); cudaFree(d.d_cell_occ);
     cudaFree(d.d_tri_index); cudaFree(d.d_cell_tris); cudaFree(d.d_cell_tris_b); cudaFree(d.d_tri_normals);
-    cudaFree(d.d_cell_tris_rel);
-    d.d_cell_tris_rel = nullptr;
+    cudaFree(d.d_ppair_start); cudaFree(d.d_pair_recs); cudaFree(d.d_pair_recs_rel);
+    d.d_ppair_start = nullptr; d.d_pair_recs = nullptr; d.d_pair_recs_rel = nullptr;
     d.rel_valid = false;
     cudaFree(d.d_pcell_start); cudaFree(d.d_pcell_occ);
     d.d_pcell_start = nullptr; d.d_pcell_occ = nullptr;
@@ -186,7 +189,9 @@ GridDev grid_dev(const cuda_trace_ctx *ctx, const DeviceState& d)
     g.pcell_occ = d.d_pcell_occ;
     g.cell_tris = d.d_cell_tris;
     g.cell_tris_b = d.d_cell_tris_b;
-    g.cell_tris_rel = d.d_cell_tris_rel;
+    g.ppair_start = d.d_ppair_start;
+    g.pair_recs = d.d_pair_recs;
+    g.pair_recs_rel = d.d_pair_recs_rel;
     g.tri_normals = d.d_tri_normals;
     g.tri = d.d_tri;
     return g;
@@ -213,6 +218,36 @@ int finish_scene_on_device(cuda_trace_ctx *ctx, DeviceState& d)
     launch_pack_cell_tris(d.d_vtx, d.d_tri, d.d_tri_index, refs, d.d_cell_tris, d.d_cell_tris_b, d.stream);
     launch_pack_normals(d.d_vtx, d.d_tri, ctx->num_tri, d.d_tri_normals, d.stream);
     ctx->launches += 2 + (refs ? 1 : 0);
+    CK(cudaGetLastError());
+    // pair records: count per padded cell -> exclusive scan -> pack
+    CK(cudaMalloc(&d.d_ppair_start, (pcells + 1) * sizeof(uint32_t)));
+    launch_pair_counts(d.d_pcell_start, pcells, d.d_ppair_start, d.stream);
+    ctx->launches++;
+    {
+        std::string err;
+        uint64_t launches = 0;
+        const int rc = exclusive_scan_u32(d.d_ppair_start, d.d_ppair_start, pcells + 1, d.stream, err, &launches);
+        ctx->launches += launches;
+        if (rc)
+            return fail(ctx, rc, err);
+    }
+    uint32_t pairs = 0;
+    CK(cudaMemcpyAsync(&pairs, d.d_ppair_start + pcells, sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    if ((uint64_t) pairs * 7 >= (1ull << 32))
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "grid too large: 7 x pair records must stay below 2^32");
+    if (&d == &ctx->dev[0])
+        ctx->num_pairs = pairs;
+    else if (ctx->num_pairs != pairs)
+        return fail(ctx, CUDA_TRACE_ERR_CUDA, "pair records differ between devices");
+    CK(cudaMalloc(&d.d_pair_recs, std::max<uint64_t>(pairs, 1) * 5 * sizeof(float4)));
+    if (pairs)
+    {
+        launch_pack_pairs(d.d_pcell_start, d.d_ppair_start, pcells, d.d_cell_tris, d.d_pair_recs, d.stream);
+        ctx->launches++;
+    }
+    else
+        CK(cudaMemsetAsync(d.d_pair_recs, 0, 5 * sizeof(float4), d.stream));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(d.stream));
     return 0;
@@ -979,6 +1014,11 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
         p.hit_u = keep_hits ? ctx->d_hit_u : nullptr;
         p.hit_v = keep_hits ? ctx->d_hit_v : nullptr;
         p.counters = d.d_counters;
+        {
+            const float one[2] = { 1.0f, 1.0f }, minus_one[2] = { -1.0f, -1.0f };
+            std::memcpy(&p.pk_one, one, sizeof(p.pk_one));
+            std::memcpy(&p.pk_minus_one, minus_one, sizeof(p.pk_minus_one));
+        }
 
         {
             const uint64_t chunks_total = (total + p.shard_chunk - 1) / p.shard_chunk;
@@ -1044,18 +1084,30 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
         const bool rel_fits = ctx->desc.num_refs <= (4ull << 20) &&
                               ((uint64_t) f->width * f->height * f->spp >= (16ull << 20) || ctx->rel_records_forced);
         const bool alternates = ortho || p.shade_mode != 0;
+        // The packed-pair test pads odd lists with a triangle at x = -1e18 that no ray can hit as long as scene and
+        // camera stay within +-1e9 (pack.cu).  Anything larger takes the scalar test of the counting instantiation.
+        bool big_coords = false;
+        for (int k = 0; k < 3; k++)
+            big_coords = big_coords || !(std::fabs(ctx->desc.aabb_min[k]) < 1.0e9f) || !(std::fabs(ctx->desc.aabb_max[k]) < 1.0e9f) ||
+                         !(std::fabs(f->cam_mat[12 + k]) < 1.0e9f);
+        if (ortho)
+            big_coords = big_coords || !(std::fabs(p.cam.ortho_half_w) < 1.0e9f) || !(std::fabs(p.cam.ortho_half_h) < 1.0e9f);
+        if (alternates && big_coords)
+            return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: the orthographic camera / shading alternates need scene and "
+                                                 "camera coordinates within +-1e9");
+        const bool count_inst = ctx->counting || big_coords; // kernel instantiation with the scalar test (+ work counters)
         if (alternates && ctx->counting)
             return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: the work counters are not available with the orthographic "
                                                  "camera / shading alternates");
         const uint32_t kvariant = alternates ? (uint32_t) kVariantMTAlt + f->variant
-                                  : (f->variant == kVariantMT && !ctx->counting && ctx->rel_records && rel_fits)
+                                  : (f->variant == kVariantMT && !count_inst && ctx->rel_records && rel_fits)
                                       ? (uint32_t) kVariantMTRel : f->variant;
         const size_t smem_bytes = trace_tiles_smem_bytes(f->spp, p.occ_smem_words);
-        const std::vector<long long> okey = { (long long) kvariant, keep_hits, ctx->counting, (long long) p.occ_mode, threads,
+        const std::vector<long long> okey = { (long long) kvariant, keep_hits, count_inst, (long long) p.occ_mode, threads,
                                               (long long) smem_bytes };
         if (okey != d.occupancy_key)
         {
-            d.blocks_per_sm = std::max(1, trace_tiles_max_blocks_per_sm(kvariant, keep_hits, ctx->counting, (int) p.occ_mode,
+            d.blocks_per_sm = std::max(1, trace_tiles_max_blocks_per_sm(kvariant, keep_hits, count_inst, (int) p.occ_mode,
                                                                         threads, smem_bytes));
             d.occupancy_key = okey;
         }
@@ -1079,20 +1131,20 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
         if (kvariant == kVariantMTRel && total)
         {
             // records relative to this frame's camera position: rebuilt (inside the timed region) when it moved
-            if (!d.d_cell_tris_rel)
-                CK(cudaMalloc(&d.d_cell_tris_rel, std::max<uint64_t>(ctx->desc.num_refs, 1) * 4 * sizeof(float4)));
+            if (!d.d_pair_recs_rel)
+                CK(cudaMalloc(&d.d_pair_recs_rel, std::max<uint64_t>(ctx->num_pairs, 1) * 7 * sizeof(float4)));
             if (!d.rel_valid || std::memcmp(d.rel_origin, p.cam.origin, sizeof(d.rel_origin)) != 0)
             {
-                launch_origin_relative_records(d.d_cell_tris, ctx->desc.num_refs, p.cam.origin, d.d_cell_tris_rel, d.stream);
+                launch_origin_relative_pairs(d.d_pair_recs, std::max<uint64_t>(ctx->num_pairs, 1), p.cam.origin, d.d_pair_recs_rel, d.stream);
                 ctx->launches++;
                 std::memcpy(d.rel_origin, p.cam.origin, sizeof(d.rel_origin));
                 d.rel_valid = true;
             }
-            p.grid.cell_tris_rel = d.d_cell_tris_rel;
+            p.grid.pair_recs_rel = d.d_pair_recs_rel;
         }
         if (total)
         {
-            launch_trace_tiles(p, kvariant, keep_hits, ctx->counting, blocks, threads, d.stream);
+            launch_trace_tiles(p, kvariant, keep_hits, count_inst, blocks, threads, d.stream);
             ctx->launches++;
         }
         if (i == 0)

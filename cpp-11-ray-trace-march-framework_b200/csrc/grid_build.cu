@@ -375,6 +375,8 @@ __global__ void sum_u32_kernel(const uint32_t *__restrict__ in, uint64_t n, unsi
         atomicAdd(total, s);
 }
 
+} // namespace
+
 int exclusive_scan_u32(const uint32_t *d_in, uint32_t *d_out, uint64_t n, cudaStream_t stream, std::string& err,
                        uint64_t *launches)
 {
@@ -402,6 +404,9 @@ int exclusive_scan_u32(const uint32_t *d_in, uint32_t *d_out, uint64_t n, cudaSt
     GB_CK(cudaGetLastError());
     return 0;
 }
+
+namespace
+{
 
 // ---- K5b: the reference pushes triangle indices in ascending order (grid.cpp:65,122) and the
 // traversal's strict "cur_t < t" keeps the FIRST of equal-t hits (grid.cpp:259), so list order is

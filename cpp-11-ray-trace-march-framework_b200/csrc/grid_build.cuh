@@ -25,4 +25,8 @@ int build_grid_device(const float *d_vtx, uint32_t num_vtx, const uint32_t *d_tr
                       uint32_t grid_res, cudaStream_t stream, GridBuildResult *out, std::string& err,
                       uint64_t *launches);
 
+// Exclusive prefix sum over n uint32 words (in place allowed); synchronises `stream` when n spans several tiles
+int exclusive_scan_u32(const uint32_t *d_in, uint32_t *d_out, uint64_t n, cudaStream_t stream, std::string& err,
+                       uint64_t *launches);
+
 } // namespace rtm

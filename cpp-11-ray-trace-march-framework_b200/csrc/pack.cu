@@ -147,33 +147,114 @@ inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned) ((n
 
 } // namespace
 
+// ---- pair records (rt_device.cuh): two triangles of a cell interleaved component by component, for the
+// packed-fp32 Moeller-Trumbore of K1 (warp_trace.cuh)
+namespace
+{
+
+__global__ void pair_count_kernel(const uint32_t *__restrict__ pcell_start, uint64_t pcells, uint32_t *__restrict__ counts)
+{
+    const uint64_t q = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > pcells)
+        return;
+    counts[q] = q < pcells ? (pcell_start[q + 1] - pcell_start[q] + 1u) / 2u : 0u;
+}
+
+// The b half of an odd list's last pair: a triangle no ray can hit.  With v0 = (-1e18, 0, 0), e1 = x, e2 = y the
+// determinant is -dir.z and u = tvec . pvec / det ~ 1e18 for every |det| >= 1e-8 (rejected by the u test,
+// triangle.h:83-85); a smaller |det| is rejected by the determinant test itself (triangle.h:77-78).  Valid for
+// scenes whose coordinates stay below ~1e9, which the launcher checks.
+__device__ __forceinline__ void dummy_triangle(float4& a, float4& b, float4& c)
+{
+    a = make_float4(-1.0e18f, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
+    b = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+    c = make_float4(0.0f, 1.0f, 0.0f, 0.0f);
+}
+
+// one thread per padded cell (lists are short: the count over 2 of the cell's references)
+__global__ void pack_pairs_kernel(const uint32_t *__restrict__ pcell_start, const uint32_t *__restrict__ ppair_start,
+                                  uint64_t pcells, const float4 *__restrict__ cell_tris, float4 *__restrict__ pair_recs)
+{
+    const uint64_t q = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= pcells)
+        return;
+    const uint32_t beg = pcell_start[q], end = pcell_start[q + 1];
+    uint64_t out = ppair_start[q];
+    for (uint32_t k = beg; k < end; k += 2, out++)
+    {
+        const float4 a0 = cell_tris[3 * (uint64_t) k + 0], a1 = cell_tris[3 * (uint64_t) k + 1], a2 = cell_tris[3 * (uint64_t) k + 2];
+        float4 b0, b1, b2;
+        if (k + 1 < end)
+        {
+            b0 = cell_tris[3 * (uint64_t) k + 3]; b1 = cell_tris[3 * (uint64_t) k + 4]; b2 = cell_tris[3 * (uint64_t) k + 5];
+        }
+        else
+            dummy_triangle(b0, b1, b2);
+        float4 *r = pair_recs + 5 * out;
+        r[0] = make_float4(a0.x, b0.x, a0.y, b0.y);
+        r[1] = make_float4(a0.z, b0.z, a1.x, b1.x);
+        r[2] = make_float4(a1.y, b1.y, a1.z, b1.z);
+        r[3] = make_float4(a2.x, b2.x, a2.y, b2.y);
+        r[4] = make_float4(a2.z, b2.z, a0.w, b0.w);
+    }
+}
+
 // Primary rays share their origin, so everything in the Moeller-Trumbore test (triangle.h:15-107) that does not
 // involve the direction is the same for every ray of a frame: tvec = orig - v0, qvec = tvec x e1, e2 . qvec.
 // Computed here once per camera position with the very expressions of the per-ray test (same operand order, no
-// contraction), so the per-ray results stay bit-identical: {tvec, tri}, {e1}, {e2}, {qvec, e2 . qvec}.
-__global__ void origin_relative_records_kernel(const float4 *__restrict__ cell_tris, uint64_t num_refs, float ox, float oy,
-                                               float oz, float4 *__restrict__ rel)
+// contraction), so the per-ray results stay bit-identical.  One thread per pair record.
+__global__ void origin_relative_pairs_kernel(const float4 *__restrict__ pair_recs, uint64_t num_pairs, float ox, float oy,
+                                             float oz, float4 *__restrict__ rel)
 {
     const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= num_refs)
+    if (k >= num_pairs)
         return;
-    const float4 ra = cell_tris[3 * k + 0], rb = cell_tris[3 * k + 1], rc = cell_tris[3 * k + 2];
-    const float tx = ox - ra.x, ty = oy - ra.y, tz = oz - ra.z;
-    const float qx = ty * rb.z - tz * rb.y;
-    const float qy = tz * rb.x - tx * rb.z;
-    const float qz = tx * rb.y - ty * rb.x;
-    rel[4 * k + 0] = make_float4(tx, ty, tz, ra.w);
-    rel[4 * k + 1] = rb;
-    rel[4 * k + 2] = rc;
-    rel[4 * k + 3] = make_float4(qx, qy, qz, rc.x * qx + rc.y * qy + rc.z * qz);
+    const float4 *r = pair_recs + 5 * k;
+    const float4 f0 = r[0], f1 = r[1], f2 = r[2], f3 = r[3], f4 = r[4];
+    float tv[2][3], q[2][3], e2q[2];
+    const float v0[2][3] = { { f0.x, f0.z, f1.x }, { f0.y, f0.w, f1.y } };
+    const float e1[2][3] = { { f1.z, f2.x, f2.z }, { f1.w, f2.y, f2.w } };
+    const float e2[2][3] = { { f3.x, f3.z, f4.x }, { f3.y, f3.w, f4.y } };
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+    {
+        const float tx = ox - v0[h][0], ty = oy - v0[h][1], tz = oz - v0[h][2];
+        const float qx = ty * e1[h][2] - tz * e1[h][1];
+        const float qy = tz * e1[h][0] - tx * e1[h][2];
+        const float qz = tx * e1[h][1] - ty * e1[h][0];
+        tv[h][0] = tx; tv[h][1] = ty; tv[h][2] = tz;
+        q[h][0] = qx; q[h][1] = qy; q[h][2] = qz;
+        e2q[h] = e2[h][0] * qx + e2[h][1] * qy + e2[h][2] * qz;
+    }
+    float4 *o = rel + 7 * k;
+    o[0] = make_float4(tv[0][0], tv[1][0], tv[0][1], tv[1][1]);
+    o[1] = make_float4(tv[0][2], tv[1][2], f1.z, f1.w);
+    o[2] = f2;
+    o[3] = f3;
+    o[4] = f4;
+    o[5] = make_float4(q[0][0], q[1][0], q[0][1], q[1][1]);
+    o[6] = make_float4(q[0][2], q[1][2], e2q[0], e2q[1]);
 }
 
-void launch_origin_relative_records(const float4 *cell_tris, uint64_t num_refs, const float origin[3], float4 *rel,
-                                    cudaStream_t stream)
+} // namespace
+
+void launch_origin_relative_pairs(const float4 *pair_recs, uint64_t num_pairs, const float origin[3], float4 *rel,
+                                  cudaStream_t stream)
 {
-    if (num_refs)
-        origin_relative_records_kernel<<<blocks_for(num_refs, 256), 256, 0, stream>>>(cell_tris, num_refs, origin[0], origin[1],
-                                                                                      origin[2], rel);
+    if (num_pairs)
+        origin_relative_pairs_kernel<<<blocks_for(num_pairs, 256), 256, 0, stream>>>(pair_recs, num_pairs, origin[0], origin[1],
+                                                                                     origin[2], rel);
+}
+
+void launch_pair_counts(const uint32_t *pcell_start, uint64_t pcells, uint32_t *counts, cudaStream_t stream)
+{
+    pair_count_kernel<<<blocks_for(pcells + 1, 256), 256, 0, stream>>>(pcell_start, pcells, counts);
+}
+
+void launch_pack_pairs(const uint32_t *pcell_start, const uint32_t *ppair_start, uint64_t pcells, const float4 *cell_tris,
+                       float4 *pair_recs, cudaStream_t stream)
+{
+    pack_pairs_kernel<<<blocks_for(pcells, 256), 256, 0, stream>>>(pcell_start, ppair_start, pcells, cell_tris, pair_recs);
 }
 
 void launch_pack_cell_tris(const float *vtx, const uint32_t *tri, const uint32_t *tri_index, uint64_t num_refs,

@@ -34,7 +34,10 @@ __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const void 
     hit.t = hit.u = hit.v = 0.0f;
     hit.tri = 0xFFFFFFFFu;
     if (COUNT && valid) cnt->rays++;
-    const bool is_hit = warp_grid_intersect<TRI_VARIANT, COUNT, OCC_MODE, RCP_GUARD>(p.grid, s_occ, o, d, valid, hit, cnt);
+    PackedUnits units;
+    units.one = p.pk_one;
+    units.minus_one = p.pk_minus_one;
+    const bool is_hit = warp_grid_intersect<TRI_VARIANT, COUNT, OCC_MODE, RCP_GUARD>(p.grid, s_occ, o, d, valid, hit, cnt, units);
     if (COUNT && is_hit) cnt->hits++;
     if (KEEP_HITS && valid)
     {

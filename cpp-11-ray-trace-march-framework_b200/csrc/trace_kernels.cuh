@@ -39,7 +39,7 @@ constexpr int kTraceMaxThreads = 1024; // launch bound (caps the kernel at 64 re
 enum { kOccGlobalBits = 0, kOccSmemBits = 1, kOccSmemBytes = 2 };
 
 // Kernel-side intersection variants: 0 / 1 are the ABI's (Moeller-Trumbore, plane + barycentric); 2 is
-// Moeller-Trumbore on origin-relative records (GridDev::cell_tris_rel) -- the launcher's choice for primary rays
+// Moeller-Trumbore on origin-relative records (GridDev::pair_recs_rel) -- the launcher's choice for primary rays
 // 3 / 4 are 0 / 1 with the reference's alternates compiled in (orthographic camera, face-normal and depth shading:
 // CameraDev::ortho, TraceParams::shade_mode) -- separate instantiations so that the live path does not carry them
 enum { kVariantMT = 0, kVariantBary = 1, kVariantMTRel = 2, kVariantMTAlt = 3, kVariantBaryAlt = 4 };
@@ -82,6 +82,9 @@ struct TraceParams
     uint32_t *hit_tri;                 // optional per-sample records (KEEP_HITS)
     float *hit_t, *hit_u, *hit_v;
     Counters *counters;                // optional (COUNT)
+    // (1.0f, 1.0f) and (-1.0f, -1.0f) as register pairs: the multiplier of the packed sums and differences in
+    // warp_trace.cuh.  Passed as data so that ptxas cannot fold them into a contracted FFMA2.
+    unsigned long long pk_one, pk_minus_one;
 };
 
 struct RayBatchParams
@@ -115,8 +118,11 @@ size_t strip_order_scratch_words(uint32_t n);
 size_t strip_order_capacity(uint32_t n, uint32_t parts);
 
 // scene packing (pack.cu)
-void launch_origin_relative_records(const float4 *cell_tris, uint64_t num_refs, const float origin[3], float4 *rel,
-                                    cudaStream_t stream);
+void launch_pair_counts(const uint32_t *pcell_start, uint64_t pcells, uint32_t *counts, cudaStream_t stream); // counts[pcells + 1]
+void launch_pack_pairs(const uint32_t *pcell_start, const uint32_t *ppair_start, uint64_t pcells, const float4 *cell_tris,
+                       float4 *pair_recs, cudaStream_t stream);
+void launch_origin_relative_pairs(const float4 *pair_recs, uint64_t num_pairs, const float origin[3], float4 *rel,
+                                  cudaStream_t stream);
 void launch_pack_cell_tris(const float *vtx, const uint32_t *tri, const uint32_t *tri_index, uint64_t num_refs,
                            float4 *cell_tris, float4 *cell_tris_b, cudaStream_t stream);
 void launch_pack_normals(const float *vtx, const uint32_t *tri, uint32_t num_tri, float4 *tri_normals,
