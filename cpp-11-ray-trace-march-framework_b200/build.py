@@ -2,7 +2,10 @@
 
     python cpp-11-ray-trace-march-framework_b200/build.py [--force]
 
-libcuda_trace.so  -- CUDA kernels + the C ABI of include/cuda_trace.h (csrc/*.cu)
+libcuda_trace.so          -- CUDA kernels + the C ABI of include/cuda_trace.h (csrc/*.cu)
+libcuda_trace_measure.so  -- measurement / self-check helpers of include/cuda_trace_measure.h (csrc/measure.cu);
+                             loaded by bench.py, tools/ and tests/ only
+librtm_host.so            -- the C++ host mirror of the reference classes (host/*.cpp)
 """
 import os
 import subprocess
@@ -18,7 +21,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
               "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-Xptxas", "-v"]
-CU_SOURCES = ["api.cu", "trace_kernels.cu", "pack.cu", "grid_build.cu", "schedule.cu", "qmc.cu", "peaks.cu"]
+CU_SOURCES = ["api.cu", "trace_kernels.cu", "pack.cu", "grid_build.cu", "schedule.cu", "qmc.cu"]
+LIB_MEASURE = os.path.join(PKG, "libcuda_trace_measure.so")
 
 
 def _newer(target, deps):
@@ -50,6 +54,21 @@ def build_cuda(force=False, verbose=False):
     cmd = [NVCC, "-shared", "-o", LIB_CUDA] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
     return LIB_CUDA
+
+
+def build_measure(force=False, verbose=False):
+    """libcuda_trace_measure.so: roofline ceilings, L2 flush, arithmetic self-check (csrc/measure.cu)."""
+    src = os.path.join(CSRC, "measure.cu")
+    deps = [src, os.path.join(CSRC, "rt_device.cuh"), os.path.join(ROOT, "include", "cuda_trace_measure.h")]
+    if not force and not _newer(LIB_MEASURE, deps):
+        return LIB_MEASURE
+    cmd = [NVCC] + NVCC_FLAGS + ["-shared", "-o", LIB_MEASURE, src, "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    return LIB_MEASURE
 
 
 HOST = os.path.join(PKG, "host")
@@ -97,7 +116,7 @@ def build_cli(force=False, verbose=False):
 
 
 def build_all(force=False, verbose=False):
-    return [build_cuda(force, verbose), build_host(force, verbose), build_cli(force, verbose)]
+    return [build_cuda(force, verbose), build_measure(force, verbose), build_host(force, verbose), build_cli(force, verbose)]
 
 
 if __name__ == "__main__":

@@ -70,7 +70,6 @@ SYMBOLS = {
     "cuda_trace_intersect_rays_brute_force": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P, _F32P, _F32P]),
     "cuda_trace_band_shares": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                          _U32P, _U32P, _U32P, _U32P, _U32P]),
-    "cuda_trace_measure_peaks": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cuda_trace_last_call_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "cuda_trace_download_strip_cycles": (C.c_int, [C.c_void_p, _U32P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "cuda_trace_ray_march": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P]),
@@ -83,7 +82,6 @@ SYMBOLS = {
     "cuda_trace_get_counters": (C.c_int, [C.c_void_p, C.POINTER(CountersC)]),
     "cuda_trace_host_alloc": (C.c_void_p, [C.c_size_t]),
     "cuda_trace_host_free": (None, [C.c_void_p]),
-    "cuda_trace_flush_l2": (C.c_int, [C.c_void_p]),
     "cuda_trace_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "cuda_trace_prepare_framebuffer": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "cuda_trace_export_framebuffer": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -149,14 +147,54 @@ def band_shares(width, height, spp, rects, world, chunk=32):
     return dict(shares=shares, gpus_in_band=gpus, band_rows=rows.value, n_bands=nb.value, pieces_per_strip=pieces.value)
 
 
+MEASURE_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcuda_trace_measure.so")
+_measure_lib = None
+
+
+def load_measure_library():
+    """dlopen libcuda_trace_measure.so (include/cuda_trace_measure.h): roofline ceilings, L2 flush, arithmetic
+    self-check.  Measurement code -- the product library does not link it."""
+    global _measure_lib
+    if _measure_lib is None:
+        if not os.path.exists(MEASURE_LIB_PATH):
+            raise RuntimeError(MEASURE_LIB_PATH + " is missing: build it with "
+                               "`python cpp-11-ray-trace-march-framework_b200/build.py`")
+        lib = C.CDLL(MEASURE_LIB_PATH)
+        lib.rtm_measure_peaks.restype = C.c_int
+        lib.rtm_measure_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        lib.rtm_measure_flush_l2.restype = C.c_int
+        lib.rtm_measure_flush_l2.argtypes = [C.c_int]
+        lib.rtm_measure_check_fast_arith.restype = C.c_int
+        lib.rtm_measure_check_fast_arith.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_int, C.c_int,
+                                                     C.POINTER(C.c_ulonglong)]
+        _measure_lib = lib
+    return _measure_lib
+
+
 def measure_peaks(device=0):
-    """-> (FP32 non-FMA T instr-flop/s, L2 read GB/s) measured on ``device`` (csrc/peaks.cu)."""
-    lib = load_library()
+    """-> (FP32 non-FMA T instr-flop/s, L2 read GB/s) measured on ``device`` (csrc/measure.cu)."""
+    lib = load_measure_library()
     a, b = C.c_double(), C.c_double()
-    rc = lib.cuda_trace_measure_peaks(device, C.byref(a), C.byref(b))
+    rc = lib.rtm_measure_peaks(device, C.byref(a), C.byref(b))
     if rc:
-        raise RuntimeError("cuda_trace_measure_peaks failed: %d" % rc)
+        raise RuntimeError("rtm_measure_peaks failed: %d" % rc)
     return a.value, b.value
+
+
+def flush_l2(device=0):
+    """Evict the L2 of ``device`` (between timed frames; synchronises the device)."""
+    rc = load_measure_library().rtm_measure_flush_l2(device)
+    if rc:
+        raise RuntimeError("rtm_measure_flush_l2 failed: %d" % rc)
+
+
+def check_fast_arith(n, seed=1, exp_lo=-40, exp_hi=40, device=0):
+    """-> (rcp, div, sqrt) mismatch counts of the range-check-free sequences against the IEEE intrinsics."""
+    bad = (C.c_ulonglong * 3)()
+    rc = load_measure_library().rtm_measure_check_fast_arith(device, n, seed, exp_lo, exp_hi, bad)
+    if rc:
+        raise RuntimeError("rtm_measure_check_fast_arith failed: %d" % rc)
+    return tuple(int(x) for x in bad)
 
 
 class PinnedImage:
@@ -186,6 +224,7 @@ class CudaTrace:
     def __init__(self, n_gpus=1, devices=None):
         self.lib = load_library()
         self.h = C.c_void_p()
+        self.devices = list(devices) if devices is not None else list(range(n_gpus))
         if devices is not None:
             arr = (C.c_int * len(devices))(*devices)
             rc = self.lib.cuda_trace_init_devices(arr, len(devices), C.byref(self.h))
@@ -397,7 +436,10 @@ class CudaTrace:
         return dict(rays=int(c.rays), cells=int(c.cells), tri_tests=int(c.tri_tests), hits=int(c.hits))
 
     def flush_l2(self):
-        self._ck(self.lib.cuda_trace_flush_l2(self.h))
+        """Measurement helper (libcuda_trace_measure.so, not the product library): evict L2 on this context's devices."""
+        self.sync()
+        for dev in self.devices:
+            flush_l2(dev)
 
     def kernel_launches(self):
         return int(self.lib.cuda_trace_kernel_launches(self.h))

@@ -69,7 +69,6 @@ struct DeviceState
     std::vector<long long> occupancy_key;  // launch configuration `blocks_per_sm` was queried for
     int blocks_per_sm = 0;
     Counters *d_counters = nullptr;
-    void *d_l2_scratch = nullptr;
     // cost-ordered scheduling (schedule.cu): cycles per strip of the last frame -> order of the next
     uint32_t *d_strip_cycles = nullptr, *d_fetch_order = nullptr, *d_order_scratch = nullptr, *d_visit_total = nullptr, *d_visit_cycles = nullptr;
     unsigned long long *d_cost_sum = nullptr;
@@ -99,6 +98,7 @@ struct cuda_trace_ctx
     bool occ_in_smem = true;
     bool rel_records = true;    // RTM_REL_RECORDS=0: always the plain records, 2: origin-relative at any frame size (experiments)
     bool rel_records_forced = false;
+    bool fast_math = true;      // RTM_FAST_MATH=0: always the range-checked intrinsics (experiments)
     int cost_order_forced = -1; // schedule.cu: -1 automatic, 0 / 1 forced by RTM_COST_ORDER (experiments)
     std::atomic<uint64_t> launches{0};
 
@@ -462,6 +462,8 @@ int cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **
     }
     if (const char *e = std::getenv("RTM_COST_ORDER"))
         ctx->cost_order_forced = std::atoi(e) != 0 ? 1 : 0;
+    if (const char *e = std::getenv("RTM_FAST_MATH"))
+        ctx->fast_math = std::atoi(e) != 0;
     *out = ctx;
     return 0;
 }
@@ -500,7 +502,7 @@ void cuda_trace_destroy(cuda_trace_ctx *ctx)
     {
         free_scene(d);
         cudaFree(d.d_smp); cudaFree(d.d_tile_rects); cudaFree(d.d_tile_prefix); cudaFree(d.d_strip_counter);
-        cudaFreeHost(d.h_cancel_seen); cudaFree(d.d_counters); cudaFree(d.d_l2_scratch);
+        cudaFreeHost(d.h_cancel_seen); cudaFree(d.d_counters);
         cudaFree(d.d_strip_cycles); cudaFree(d.d_fetch_order); cudaFree(d.d_cost_sum); cudaFree(d.d_order_scratch);
         cudaFree(d.d_visit_total); cudaFree(d.d_visit_cycles);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
@@ -932,6 +934,16 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
         p.cam.aspect = f->aspect;
         p.cam.width_f = (float) f->width;
         p.cam.height_f = (float) f->height;
+        {
+            // frame constants of the range-check-free divisions (rt_device.cuh): valid while every operand and
+            // quotient of generate_ray and of the DDA set-up is an ordinary normal number
+            p.cam.inv_width = 1.0f / p.cam.width_f;
+            p.cam.inv_height = 1.0f / p.cam.height_f;
+            p.cam.inv_aspect = 1.0f / f->aspect;
+            const auto ordinary = [](float x) { return std::fabs(x) >= 0x1p-20f && std::fabs(x) <= 0x1p20f; };
+            p.cam.fast_math = (ctx->fast_math && ordinary(f->fov_xs) && ordinary(f->aspect) && ordinary(ctx->desc.cell_wdh) &&
+                               f->width <= (1u << 20) && f->height <= (1u << 20)) ? 1u : 0u;
+        }
         p.width = f->width;
         p.height = f->height;
         p.spp = f->spp;
@@ -1441,21 +1453,6 @@ void cuda_trace_host_free(void *p)
 {
     if (p)
         cudaFreeHost(p);
-}
-
-int cuda_trace_flush_l2(cuda_trace_ctx *ctx)
-{
-    if (!ctx)
-        return CUDA_TRACE_ERR_ARG;
-    const size_t bytes = 256u << 20;
-    for (DeviceState& d : ctx->dev)
-    {
-        CK(cudaSetDevice(d.ordinal));
-        if (!d.d_l2_scratch)
-            CK(cudaMalloc(&d.d_l2_scratch, bytes));
-        CK(cudaMemsetAsync(d.d_l2_scratch, 0xA5, bytes, d.stream));
-    }
-    return 0;
 }
 
 int cuda_trace_qmc_sequence(cuda_trace_ctx *ctx, uint32_t kind, uint32_t scramble, const uint32_t *perm,

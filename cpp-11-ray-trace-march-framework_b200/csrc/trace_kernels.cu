@@ -37,7 +37,7 @@ __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const void 
     PackedUnits units;
     units.one = p.pk_one;
     units.minus_one = p.pk_minus_one;
-    const bool is_hit = warp_grid_intersect<TRI_VARIANT, COUNT, OCC_MODE, RCP_GUARD>(p.grid, s_occ, o, d, valid, hit, cnt, units);
+    const bool is_hit = warp_grid_intersect<TRI_VARIANT, COUNT, OCC_MODE, RCP_GUARD>(p.grid, s_occ, o, d, valid, hit, cnt, units, p.cam.fast_math != 0);
     if (COUNT && is_hit) cnt->hits++;
     if (KEEP_HITS && valid)
     {

@@ -216,11 +216,6 @@ int cuda_trace_qmc_cranley_patterson(cuda_trace_ctx *ctx, const double *x, doubl
 int cuda_trace_set_counting(cuda_trace_ctx *ctx, int enable);
 int cuda_trace_get_counters(cuda_trace_ctx *ctx, cuda_trace_counters *out);
 
-/* Measured ceilings for the roofline figures: FP32 throughput without fused multiply-add (the
- * kernels are built -fmad=false) in T instr-flop/s, and L2 read bandwidth on an L2-resident buffer in GB/s.
- * A micro-benchmark (~0.2 s); no context needed. */
-int cuda_trace_measure_peaks(int device, double *fp32_nonfma_tflops, double *l2_read_gbps);
-
 /* Host-clock marks of the last cuda_trace_tiles call, in ms since its entry: [0] work submitted, [1] trace stream
  * drained, [2] read-back copies drained (overlapped mode), [3] return, [4] host set-up done, [5] / [6] before /
  * after the launch of the first device's trace kernel.  Diagnostics for the end-to-end figure. */
@@ -245,10 +240,6 @@ int cuda_trace_download_strip_cycles(cuda_trace_ctx *ctx, uint32_t *cycles, uint
  * (the driver stages it), only slower.  Free with cuda_trace_host_free. */
 void *cuda_trace_host_alloc(size_t bytes);
 void  cuda_trace_host_free(void *p);
-
-/* Measurement helper: evict the scene from L2 by overwriting a scratch buffer larger than L2
- * (256 MiB cudaMemsetAsync on every device's stream).  Not part of the traced work. */
-int cuda_trace_flush_l2(cuda_trace_ctx *ctx);
 
 /* How many kernels this library has launched since cuda_trace_init (all devices) */
 uint64_t cuda_trace_kernel_launches(const cuda_trace_ctx *ctx);

@@ -27,6 +27,19 @@ def test_header_symbols_all_exported_and_bound():
     assert sorted(capi.SYMBOLS) == names
 
 
+def test_measure_library_exports_its_header():
+    """libcuda_trace_measure.so (measurement / self-check, not the product) loads and exports what
+    include/cuda_trace_measure.h declares; the product header declares none of it."""
+    text = open(os.path.join(ROOT, "include", "cuda_trace_measure.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(rtm_measure_[a-z0-9_]+)\s*\(", text)))
+    assert names == ["rtm_measure_check_fast_arith", "rtm_measure_flush_l2", "rtm_measure_peaks"]
+    lib = pkg("capi").load_measure_library()
+    for n in names:
+        assert hasattr(lib, n), n
+    assert not any("measure" in n or "flush_l2" in n for n in declared_symbols())
+
+
 def test_struct_layouts_match_header():
     capi = pkg("capi")
     assert C.sizeof(capi.Frame) == 7 * 4 + 16 * 4
