@@ -19,6 +19,8 @@ namespace
 {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
+// the 48 KB a kernel gets without opting in cover static + dynamic shared memory; K1 has ~21 KB of static
+constexpr size_t kOptInDynamicSmem = 24 * 1024;
 
 // One sample per lane; ALL lanes of the warp call this together (valid == false: no ray)
 template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE, bool RCP_GUARD>
@@ -34,10 +36,10 @@ __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const void 
     hit.t = hit.u = hit.v = 0.0f;
     hit.tri = 0xFFFFFFFFu;
     if (COUNT && valid) cnt->rays++;
-    PackedUnits units;
-    units.one = p.pk_one;
-    units.minus_one = p.pk_minus_one;
-    const bool is_hit = warp_grid_intersect<TRI_VARIANT, COUNT, OCC_MODE, RCP_GUARD>(p.grid, s_occ, o, d, valid, hit, cnt, units, p.cam.fast_math != 0);
+    PackedUnits pku;
+    pku.one = p.pk_one;
+    pku.minus_one = p.pk_minus_one;
+    const bool is_hit = warp_grid_intersect<TRI_VARIANT, COUNT, OCC_MODE, RCP_GUARD>(p.grid, s_occ, o, d, valid, hit, cnt, pku, p.cam.fast_math != 0);
     if (COUNT && is_hit) cnt->hits++;
     if (KEEP_HITS && valid)
     {
@@ -110,6 +112,10 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
     const uint32_t lane = threadIdx.x & 31u;
     const float spp_f = (float) p.spp;
     Counters cnt = { 0, 0, 0, 0 };
+    __shared__ float4 s_rgb[kTraceMaxThreads]; // one colour sample per lane (the in-order sum below)
+    PackedUnits pku;
+    pku.one = p.pk_one;
+    pku.minus_one = p.pk_minus_one;
 
     const uint32_t slots = p.strip_w * p.strip_h;
     // finished pieces not yet published (see the band publication below): lane b holds those of row band b
@@ -208,16 +214,26 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
                     continue;
                 const uint32_t px = bx0 + ox, py = by0 + oy;
                 const float3 rgb = trace_sample<VARIANT, KEEP_HITS, COUNT, OCC_MODE, RCP_GUARD>(p, s_occ, active, px, py, s, s_smp, &cnt);
-                // col += sample, smp = 0..N-1 in order (renderer.cpp:87-122)
-                float3 acc = make_float3(0.0f, 0.0f, 0.0f);
-                const uint32_t base = pl * p.spp;
+                // col += sample, smp = 0..N-1 in order (renderer.cpp:87-122).  The samples of a pixel sit in
+                // consecutive lanes; they go through shared memory -- one 16-byte store per lane, one broadcast
+                // load per term -- and every lane of the pixel adds them up in sample order (red and green as one
+                // packed add): a third of the instructions of a shuffle per channel and term.
+                s_rgb[threadIdx.x] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
+                __syncwarp();
+                f32x2 acc_rg = pk2(0.0f, 0.0f);
+                float acc_b = 0.0f;
+                // (lanes beyond the round's last pixel read that pixel's slots: inside their warp's 32)
+                const float4 *mine = s_rgb + (threadIdx.x & ~31u) + min(pl, ppr - 1u) * p.spp;
                 for (uint32_t k = 0; k < p.spp; k++)
                 {
-                    const int src = (int) ((base + k) & 31u);
-                    acc.x += __shfl_sync(kFull, rgb.x, src);
-                    acc.y += __shfl_sync(kFull, rgb.y, src);
-                    acc.z += __shfl_sync(kFull, rgb.z, src);
+                    const float4 v = mine[k];
+                    acc_rg = add2(pk2(v.x, v.y), acc_rg, pku);
+                    acc_b += v.z;
                 }
+                __syncwarp();
+                float3 acc;
+                unpk2(acc_rg, acc.x, acc.y);
+                acc.z = acc_b;
                 if (active && s == 0)
                     p.framebuffer[(size_t) py * p.width + px] = resolve_pixel(acc, spp_f, p.gamma != 0);
             }
@@ -440,7 +456,7 @@ __global__ void sample_table_kernel(float2 *smp, uint32_t spp)
 template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE, bool RCP_GUARD, bool BANDS>
 void launch_instance(const TraceParams& p, int grid_blocks, int threads, size_t smem, cudaStream_t stream)
 {
-    if (smem > 48 * 1024)
+    if (smem > kOptInDynamicSmem)
     {
         // opt in to large dynamic shared memory once per device and size, not on every launch
         static size_t opted_in[64] = {};
@@ -487,7 +503,7 @@ template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE>
 int occupancy_mode(int threads, size_t smem)
 {
     int n = 0;
-    if (smem > 48 * 1024)
+    if (smem > kOptInDynamicSmem)
         cudaFuncSetAttribute(trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_tiles_kernel<VARIANT, KEEP_HITS, COUNT, OCC_MODE, true, true>, threads, smem);
