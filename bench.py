@@ -322,6 +322,13 @@ class GpuWorkload:
         e2e_s = 0.0
         kernel_ms = np.zeros(steps, np.float64)
         marks = np.zeros(7, np.float64)
+        # one untimed call first: the completion targets of the overlapped read-back are computed once per layout
+        if rank == 0:
+            ct.trace_tiles(self.frame, self.rects, out=self.host_fb)
+        else:
+            ct.trace_tiles_async(self.frame, self.rects)
+            ct.sync()
+        group.barrier()
         for i in range(steps):
             ct.flush_l2()
             ct.sync()

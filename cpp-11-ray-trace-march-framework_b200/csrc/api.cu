@@ -62,10 +62,12 @@ struct DeviceState
     uint4 *d_tile_rects = nullptr;
     uint32_t *d_tile_prefix = nullptr;
     uint32_t tile_cap = 0;
-    uint32_t *d_strip_counter = nullptr;
-    uint32_t *d_cancel = nullptr;          // = d_strip_counter + 1 (zeroed together, one memset per frame)
-    uint32_t *h_cancel_seen = nullptr;     // page-locked: the cancel flag as the frame's kernel left it
-    std::vector<uint32_t> layout_sig;      // tile list the device copies d_tile_rects / d_tile_prefix hold
+    uint32_t *d_strip_counter = nullptr;   // {strip counter, pad to 128 B, this GPU's band piece counts}: one memset per frame
+    uint32_t *d_cancel = nullptr;          // behind them and never cleared: the sequence number of the frame to cancel
+    uint32_t *h_cancel_seen = nullptr;     // page-locked + mapped: the kernel stores its frame number here when it saw the request
+    uint32_t *d_cancel_seen = nullptr;     // device view of h_cancel_seen
+    uint32_t launched_seq = 0;             // sequence number of the frame in flight on this device
+    uint64_t layout_serial = 0;            // FramePlan the device copies d_tile_rects / d_tile_prefix hold
     std::vector<long long> occupancy_key;  // launch configuration `blocks_per_sm` was queried for
     int blocks_per_sm = 0;
     Counters *d_counters = nullptr;
@@ -74,8 +76,40 @@ struct DeviceState
     unsigned long long *d_cost_sum = nullptr;
     uint32_t order_cap = 0;
     bool order_valid = false;
-    std::vector<uint32_t> order_signature;
+    std::vector<uint64_t> order_signature; // plan serial + shard the recorded strip costs belong to
+    uint32_t order_strips = 0;             // strips of this shard the recorded costs cover
     bool frame_pending = false;
+    bool order_followup = false, order_followup_used = false; // this frame recorded strip costs (through the previous order)
+};
+
+} // namespace
+
+namespace
+{
+
+// Tuning switches, read ONCE in cuda_trace_init (experiments and tests; every default is the measured best)
+struct Tuning
+{
+    int strip_pixels = 0;  // RTM_STRIP_PIXELS = 2 | 4 | 8 | 16 | 32 pixels per strip (0: by sample count)
+    int split_parts = 0;   // RTM_SPLIT_PARTS = 1 | 2 pieces per expensive strip (0: by strip size)
+    int occ_mode = -1;     // RTM_OCC_MODE = 0 | 1 | 2 home of the occupancy map (-1: by grid size)
+    int threads = 0;       // RTM_THREADS = CTA size (0: by frame size)
+    int band_flush = 0;    // RTM_BAND_FLUSH = 1..8 strips a warp holds before publishing (0: by frame size)
+    int shard_chunk = 0;   // RTM_SHARD_CHUNK = strips per deal when sharding (0: 32)
+    bool force_bands = false; // RTM_FORCE_BANDS: publish band completion without a host buffer
+};
+
+// What a frame's tile list turns into.  Kept between calls: a viewer renders the same layout every frame.
+struct FramePlan
+{
+    uint64_t serial = 0; // changes whenever the plan is rebuilt (devices compare serials, not tile lists)
+    uint32_t width = 0, height = 0, spp = 0;
+    std::vector<cuda_trace_tile_rect> tiles;
+    uint32_t strip_w = 0, strip_h = 0, split_parts = 1;
+    std::vector<uint4> rects;
+    std::vector<uint32_t> prefix; // first strip id of each tile, + total
+    uint64_t total = 0;           // strips
+    bool covers_frame = false;    // the tiles partition the whole frame (no gap, no overlap)
 };
 
 } // namespace
@@ -84,7 +118,11 @@ struct cuda_trace_ctx
 {
     std::vector<DeviceState> dev;
     std::string err;
-    std::mutex cancel_mtx;
+    std::recursive_mutex api_mtx; // entry points that use the streams / the error slot are serialised (not cancel)
+    Tuning tune;
+    FramePlan plan;
+    std::atomic<uint32_t> frame_seq{0}, cancel_seq{0}; // cancel names the frame it is meant for
+    bool band_dirty = false;      // a launch failed half way: re-read the band counters before the next overlapped frame
 
     bool have_scene = false;
     cuda_trace_grid_desc desc;
@@ -112,10 +150,11 @@ struct cuda_trace_ctx
     // counter once per finished strip; band_expected is the running total rank 0 waits for.
     uint32_t band_rows = 1, n_bands = 1;
     uint32_t band_expected[kMaxBands] = {};
-    std::vector<uint32_t> band_inc_sig;
+    std::vector<uint64_t> band_inc_sig;
     uint32_t band_inc[kMaxBands] = {};
     std::vector<std::array<uint32_t, kMaxBands>> band_share; // per participating GPU: its pieces of strips per band
     bool copy_pending = false;
+    bool two_level = false;       // this frame's band counters are read outside the GPU that bumps them (see plan_band_counts)
     bool overlap_d2h = true;      // RTM_OVERLAP_D2H=0 disables
     bool shard_signals = false;   // cuda_trace_set_shard_signals: other ranks bump the counters too
     int (*wait_value32)(cudaStream_t, unsigned long long, unsigned int, unsigned int) = nullptr;
@@ -293,6 +332,7 @@ int ensure_framebuffer(cuda_trace_ctx *ctx, uint32_t w, uint32_t h)
     ctx->d_fb = nullptr;
     CK(cudaMalloc(&ctx->d_fb, fb_alloc_bytes(w, h)));
     CK(cudaMemsetAsync(ctx->d_fb, 0, fb_alloc_bytes(w, h), ctx->dev[0].stream));
+    CK(cudaStreamSynchronize(ctx->dev[0].stream)); // the zeroed band counters are in place before any stream waits on them
     ctx->fb_w = w;
     ctx->fb_h = h;
     std::memset(ctx->band_expected, 0, sizeof(ctx->band_expected));
@@ -312,8 +352,9 @@ double ms_since(std::chrono::steady_clock::time_point t0)
 }
 
 // Row bands of the overlapped read-back: ~1 MB of pixels per band (a DMA that size runs at full PCIe rate; the
-// last band's copy is the exposed tail), at most kMaxBands; a small frame is one band -- one wait and one copy
-// instead of dozens of driver calls.  A band is never lower than a strip.
+// last band's copy is the exposed tail), at most kMaxBands; a small frame is one band.  (Finer bands were measured
+// on the 1 MB frame of C1: 8 bands of 128 KB take 54 us to drain against 25 us for the single copy -- every
+// device-to-host copy costs ~7 us on its own.)  A band is never lower than a strip.
 void band_layout(uint32_t width, uint32_t height, uint32_t strip_h, uint32_t& band_rows, uint32_t& n_bands)
 {
     const uint64_t frame_bytes = (uint64_t) width * height * sizeof(uint32_t);
@@ -417,13 +458,14 @@ int cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **
             (e = cudaEventCreateWithFlags(&d.ev_order, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&d.ev_copy, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreate(&d.ev_begin)) != cudaSuccess || (e = cudaEventCreate(&d.ev_end)) != cudaSuccess ||
-            (e = cudaMalloc(&d.d_strip_counter, (32 + kMaxBands) * sizeof(uint32_t))) != cudaSuccess || // {strip counter, cancel flag, pad to 128 B, band piece counts}
-            (e = cudaHostAlloc(&d.h_cancel_seen, sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_strip_counter, (32 + kMaxBands + 32) * sizeof(uint32_t))) != cudaSuccess || // {strip counter, pad to 128 B | band piece counts | cancel word}
+            (e = cudaHostAlloc(&d.h_cancel_seen, sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable)) != cudaSuccess ||
+            (e = cudaHostGetDevicePointer((void **) &d.d_cancel_seen, d.h_cancel_seen, 0)) != cudaSuccess ||
             (e = cudaMalloc(&d.d_counters, sizeof(Counters))) != cudaSuccess ||
-            (e = cudaMemset(d.d_strip_counter, 0, (32 + kMaxBands) * sizeof(uint32_t))) != cudaSuccess ||
+            (e = cudaMemset(d.d_strip_counter, 0, (32 + kMaxBands + 32) * sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMemset(d.d_counters, 0, sizeof(Counters))) != cudaSuccess)
             return bail(std::string("device set-up: ") + cudaGetErrorString(e), CUDA_TRACE_ERR_CUDA);
-        d.d_cancel = d.d_strip_counter + 1;
+        d.d_cancel = d.d_strip_counter + 32 + kMaxBands; // outside the per-frame memset
         *d.h_cancel_seen = 0;
         if (i > 0)
         {
@@ -442,7 +484,7 @@ int cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **
     }
     if ((e = cudaHostAlloc(&ctx->pinned_cancel_src, sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
         return bail(std::string("cudaHostAlloc: ") + cudaGetErrorString(e), CUDA_TRACE_ERR_CUDA);
-    *ctx->pinned_cancel_src = 1;
+    *ctx->pinned_cancel_src = 0;
     {
         // stream-ordered "wait until *addr >= value" (driver API), used by the overlapped read-back
         void *fn = nullptr;
@@ -455,6 +497,7 @@ int cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **
         if (const char *e = std::getenv("RTM_OVERLAP_D2H"))
             ctx->overlap_d2h = std::atoi(e) != 0;
     }
+    // Tuning switches are read here, once per context (experiments and tests; every default is the measured best)
     if (const char *e = std::getenv("RTM_REL_RECORDS"))
     {
         ctx->rel_records = std::atoi(e) != 0;
@@ -464,6 +507,27 @@ int cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **
         ctx->cost_order_forced = std::atoi(e) != 0 ? 1 : 0;
     if (const char *e = std::getenv("RTM_FAST_MATH"))
         ctx->fast_math = std::atoi(e) != 0;
+    if (const char *e = std::getenv("RTM_STRIP_PIXELS"))
+    {
+        const int px = std::atoi(e);
+        if (px == 2 || px == 4 || px == 8 || px == 16 || px == 32)
+            ctx->tune.strip_pixels = px;
+    }
+    if (const char *e = std::getenv("RTM_SPLIT_PARTS"))
+        ctx->tune.split_parts = (std::atoi(e) == 1 || std::atoi(e) == 2) ? std::atoi(e) : 0;
+    if (const char *e = std::getenv("RTM_OCC_MODE"))
+        ctx->tune.occ_mode = (std::atoi(e) >= 0 && std::atoi(e) <= 2) ? std::atoi(e) : -1;
+    if (const char *e = std::getenv("RTM_THREADS"))
+    {
+        const int t = std::atoi(e);
+        if (t >= 32 && t <= 1024 && t % 32 == 0)
+            ctx->tune.threads = t;
+    }
+    if (const char *e = std::getenv("RTM_BAND_FLUSH"))
+        ctx->tune.band_flush = std::min(64, std::max(1, std::atoi(e)));
+    if (const char *e = std::getenv("RTM_SHARD_CHUNK"))
+        ctx->shard_chunk = (uint32_t) std::max(1, std::atoi(e));
+    ctx->tune.force_bands = std::getenv("RTM_FORCE_BANDS") != nullptr;
     *out = ctx;
     return 0;
 }
@@ -528,12 +592,11 @@ int cuda_trace_set_shard(cuda_trace_ctx *ctx, uint32_t rank, uint32_t world)
 {
     if (!ctx)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     if (world == 0 || rank >= world)
         return fail(ctx, CUDA_TRACE_ERR_ARG, "set_shard: need rank < world");
     ctx->shard_rank = rank;
     ctx->shard_world = world;
-    if (const char *e = std::getenv("RTM_SHARD_CHUNK")) // tuning override (experiments only)
-        ctx->shard_chunk = (uint32_t) std::max(1, std::atoi(e));
     return 0;
 }
 
@@ -541,6 +604,7 @@ int cuda_trace_set_shard_signals(cuda_trace_ctx *ctx, int enable)
 {
     if (!ctx)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     ctx->shard_signals = enable != 0;
     return 0;
 }
@@ -552,6 +616,7 @@ int cuda_trace_upload_scene(cuda_trace_ctx *ctx, const float *vertices, uint32_t
     int rc = check_mesh_args(ctx, vertices, num_vertices, triangles, num_triangles);
     if (rc)
         return rc;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     if (grid_res == 0)
         return fail(ctx, CUDA_TRACE_ERR_ARG, "upload_scene: grid_res must be > 0 (grid.cpp:16)");
     if ((rc = cuda_trace_sync(ctx)))
@@ -601,6 +666,7 @@ int cuda_trace_upload_scene_with_grid(cuda_trace_ctx *ctx, const float *vertices
     int rc = check_mesh_args(ctx, vertices, num_vertices, triangles, num_triangles);
     if (rc)
         return rc;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     if (!desc || !cell_offset || (!tri_index && desc->num_refs))
         return fail(ctx, CUDA_TRACE_ERR_ARG, "upload_scene_with_grid: null grid arrays");
     const uint64_t cells = (uint64_t) desc->dim[0] * desc->dim[1] * desc->dim[2];
@@ -648,6 +714,7 @@ int cuda_trace_download_grid(cuda_trace_ctx *ctx, cuda_trace_grid_desc *desc, ui
 {
     if (!ctx || !desc)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     if (!ctx->have_scene)
         return fail(ctx, CUDA_TRACE_ERR_NO_SCENE, "download_grid: no scene uploaded");
     *desc = ctx->desc;
@@ -678,6 +745,7 @@ int cuda_trace_prepare_framebuffer(cuda_trace_ctx *ctx, uint32_t width, uint32_t
 {
     if (!ctx || width == 0 || height == 0)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     int rc = ensure_framebuffer(ctx, width, height);
     if (rc)
         return rc;
@@ -689,6 +757,7 @@ int cuda_trace_export_framebuffer(cuda_trace_ctx *ctx, void *handle64)
 {
     if (!ctx || !handle64)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     if (!ctx->d_fb || ctx->fb_imported)
         return fail(ctx, CUDA_TRACE_ERR_ARG, "export_framebuffer: call cuda_trace_prepare_framebuffer first");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -703,6 +772,7 @@ int cuda_trace_import_framebuffer(cuda_trace_ctx *ctx, const void *handle64, uin
 {
     if (!ctx || !handle64 || width == 0 || height == 0)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     int rc = cuda_trace_sync(ctx);
     if (rc)
         return rc;
@@ -730,473 +800,598 @@ int cuda_trace_set_counting(cuda_trace_ctx *ctx, int enable)
 {
     if (!ctx)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     ctx->counting = enable != 0;
     return 0;
 }
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------- one frame
+// cuda_trace_tiles in five steps, each its own function:
+//   check_frame_args      everything that can be refused is refused BEFORE any state changes
+//   update_plan           tile list -> strips (cached while the layout repeats)
+//   plan_band_counts      completion targets of the overlapped read-back for this layout (cached)
+//   launch_on_device      per-GPU buffers, kernel parameters, launch configuration, launch, cost-order follow-up
+//   enqueue_band_copies   copy stream: wait for a row band, ship it to the host buffer
+namespace
+{
+
+constexpr uint32_t kMaxSpp = 4096; // sample table in shared memory: 32 KB next to the occupancy map
+
+struct FrameKind
+{
+    bool keep_hits, ortho, alternates, count_inst;
+    uint32_t shade_mode;
+};
+
+int check_frame_args(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const cuda_trace_tile_rect *tiles, uint32_t n_tiles,
+                     FrameKind& kind)
+{
+    if (!ctx->have_scene)
+        return fail(ctx, CUDA_TRACE_ERR_NO_SCENE, "trace_tiles: upload a scene first");
+    if (f->width == 0 || f->height == 0 || f->spp == 0 || f->variant > 1)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: bad frame description");
+    if (f->spp > kMaxSpp)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: at most " + std::to_string(kMaxSpp) + " samples per pixel");
+    if ((uint64_t) f->width * f->height >= (1ull << 32))
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: frame too large");
+    for (uint32_t i = 0; i < n_tiles; i++)
+    {
+        const cuda_trace_tile_rect& t = tiles[i];
+        if (t.x0 > t.x1 || t.y0 > t.y1 || t.x1 > f->width || t.y1 > f->height)
+            return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: tile " + std::to_string(i) + " outside the frame");
+    }
+    if (ctx->fb_imported && (ctx->fb_w != f->width || ctx->fb_h != f->height))
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "frame size differs from the imported framebuffer");
+    kind.keep_hits = (f->flags & CUDA_TRACE_FLAG_KEEP_HITS) != 0;
+    kind.ortho = (f->flags & CUDA_TRACE_FLAG_ORTHO) != 0;
+    kind.shade_mode = (f->flags & CUDA_TRACE_FLAG_SHADE_FACE_NORMAL) ? 1u : ((f->flags & CUDA_TRACE_FLAG_SHADE_DEPTH) ? 2u : 0u);
+    kind.alternates = kind.ortho || kind.shade_mode != 0;
+    // The packed-pair test pads odd lists with a triangle at x = -1e18 that no ray can hit as long as scene and
+    // camera stay within +-1e9 (pack.cu).  Anything larger takes the scalar test of the counting instantiation.
+    bool big_coords = false;
+    for (int k = 0; k < 3; k++)
+        big_coords = big_coords || !(std::fabs(ctx->desc.aabb_min[k]) < 1.0e9f) || !(std::fabs(ctx->desc.aabb_max[k]) < 1.0e9f) ||
+                     !(std::fabs(f->cam_mat[12 + k]) < 1.0e9f);
+    if (kind.ortho)
+        big_coords = big_coords || !(std::fabs(f->fov_xs) < 1.0e9f) || !(std::fabs(f->fov_xs / f->aspect) < 1.0e9f);
+    if (kind.alternates && big_coords)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: the orthographic camera / shading alternates need scene and "
+                                             "camera coordinates within +-1e9");
+    if (kind.alternates && ctx->counting)
+        return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: the work counters are not available with the orthographic "
+                                             "camera / shading alternates");
+    kind.count_inst = ctx->counting || big_coords; // kernel instantiation with the scalar test (+ work counters)
+    return 0;
+}
+
+// Tile list -> strips (strip_w x strip_h pixel blocks, clipped to the tile).  No device work, no context state
+// other than ctx->plan; returns an error only for layouts with too many strips.
+int update_plan(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const cuda_trace_tile_rect *tiles, uint32_t n_tiles)
+{
+    FramePlan& pl = ctx->plan;
+    if (pl.serial && pl.width == f->width && pl.height == f->height && pl.spp == f->spp && pl.tiles.size() == n_tiles &&
+        (n_tiles == 0 || std::memcmp(pl.tiles.data(), tiles, sizeof(cuda_trace_tile_rect) * n_tiles) == 0))
+        return 0;
+    FramePlan np;
+    np.width = f->width; np.height = f->height; np.spp = f->spp;
+    np.tiles.assign(tiles, tiles + n_tiles);
+    strip_size_for_spp(f->spp, (uint64_t) f->width * f->height * f->spp, np.strip_w, np.strip_h);
+    if (const int px = ctx->tune.strip_pixels)
+    {
+        np.strip_w = px >= 32 ? 8 : (px >= 8 ? 4 : 2);
+        np.strip_h = px >= 16 ? 4 : (px >= 4 ? 2 : 1);
+    }
+    np.split_parts = strip_split_parts(np.strip_w, np.strip_h, f->spp);
+    if (ctx->tune.split_parts == 1 || (ctx->tune.split_parts == 2 && np.split_parts >= 2))
+        np.split_parts = (uint32_t) ctx->tune.split_parts;
+    np.rects.resize(n_tiles);
+    np.prefix.assign(n_tiles + 1, 0);
+    uint64_t total = 0, area = 0;
+    for (uint32_t i = 0; i < n_tiles; i++)
+    {
+        const cuda_trace_tile_rect& t = tiles[i];
+        np.rects[i] = make_uint4(t.x0, t.y0, t.x1, t.y1);
+        np.prefix[i] = (uint32_t) total;
+        total += (uint64_t) ((t.x1 - t.x0 + np.strip_w - 1) / np.strip_w) * ((t.y1 - t.y0 + np.strip_h - 1) / np.strip_h);
+        area += (uint64_t) (t.x1 - t.x0) * (t.y1 - t.y0);
+        if (total >= (1ull << 32))
+            return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: too many strips");
+    }
+    np.prefix[n_tiles] = (uint32_t) total;
+    np.total = total;
+    // "the tiles cover the frame" exactly: areas add up to the frame AND no two tiles overlap
+    bool disjoint = area == (uint64_t) f->width * f->height;
+    for (uint32_t i = 0; disjoint && i < n_tiles; i++)
+        for (uint32_t k = i + 1; k < n_tiles; k++)
+        {
+            const cuda_trace_tile_rect &a = tiles[i], &b = tiles[k];
+            if (a.x0 < b.x1 && b.x0 < a.x1 && a.y0 < b.y1 && b.y0 < a.y1 && a.x0 < a.x1 && a.y0 < a.y1 && b.x0 < b.x1 && b.y0 < b.y1)
+            {
+                disjoint = false;
+                break;
+            }
+        }
+    np.covers_frame = disjoint;
+    np.serial = pl.serial + 1;
+    pl = std::move(np);
+    return 0;
+}
+
+// Completion targets of the overlapped read-back (cached per layout): ctx->band_inc[b] = what a frame adds to the
+// counter of band b, ctx->band_share[q][b] = pieces GPU q contributes
+void plan_band_counts(cuda_trace_ctx *ctx)
+{
+    const FramePlan& pl = ctx->plan;
+    band_layout(pl.width, pl.height, pl.strip_h, ctx->band_rows, ctx->n_bands);
+    const uint32_t participants = ctx->shard_world * (uint32_t) ctx->dev.size();
+    // Two levels (ctx->two_level): every GPU counts its pieces per band in its own memory (release at GPU scope:
+    // cheap) and the warp that completes the GPU's share bumps the band counter once, at system scope -- whenever
+    // the reader is another GPU or a copy engine.  One level only for counters nobody outside this GPU reads.
+    const uint64_t two_level = ctx->two_level ? 1u : 0u;
+    const std::vector<uint64_t> sig = { pl.serial, participants, ctx->shard_chunk, two_level };
+    if (sig == ctx->band_inc_sig)
+        return;
+    band_shares(pl.rects, pl.prefix, pl.strip_w, pl.strip_h, ctx->band_rows, pl.split_parts, ctx->shard_chunk, participants,
+                ctx->band_share, ctx->band_inc);
+    if (!two_level)
+        for (int b = 0; b < kMaxBands; b++)
+            ctx->band_inc[b] = ctx->band_share[0][b];
+    ctx->band_inc_sig = sig;
+}
+
+// After a launch failed half way the band counters on the device and the totals kept here may disagree: wait for
+// whatever is in flight and re-read them (the counters are monotone and never reset)
+int resync_band_counters(cuda_trace_ctx *ctx)
+{
+    for (DeviceState& d : ctx->dev)
+    {
+        CK(cudaSetDevice(d.ordinal));
+        CK(cudaStreamSynchronize(d.stream));
+    }
+    if (ctx->d_fb)
+    {
+        CK(cudaSetDevice(ctx->dev[0].ordinal));
+        CK(cudaMemcpy(ctx->band_expected, band_counters(ctx), sizeof(ctx->band_expected), cudaMemcpyDeviceToHost));
+    }
+    ctx->band_dirty = false;
+    return 0;
+}
+
+int ensure_hit_buffers(cuda_trace_ctx *ctx, const cuda_trace_frame *f)
+{
+    const uint64_t need = (uint64_t) f->width * f->height * f->spp;
+    CK(cudaSetDevice(ctx->dev[0].ordinal));
+    if (need > ctx->hit_cap)
+    {
+        cudaFree(ctx->d_hit_tri); cudaFree(ctx->d_hit_t); cudaFree(ctx->d_hit_u); cudaFree(ctx->d_hit_v);
+        ctx->d_hit_tri = nullptr; ctx->d_hit_t = ctx->d_hit_u = ctx->d_hit_v = nullptr;
+        ctx->hit_cap = 0;
+        CK(cudaMalloc(&ctx->d_hit_tri, need * 4));
+        CK(cudaMalloc(&ctx->d_hit_t, need * 4));
+        CK(cudaMalloc(&ctx->d_hit_u, need * 4));
+        CK(cudaMalloc(&ctx->d_hit_v, need * 4));
+        ctx->hit_cap = need;
+    }
+    ctx->hit_count = need;
+    // samples outside the requested tiles read as "miss"
+    CK(cudaMemsetAsync(ctx->d_hit_tri, 0xFF, need * 4, ctx->dev[0].stream));
+    CK(cudaMemsetAsync(ctx->d_hit_t, 0, need * 4, ctx->dev[0].stream));
+    CK(cudaMemsetAsync(ctx->d_hit_u, 0, need * 4, ctx->dev[0].stream));
+    CK(cudaMemsetAsync(ctx->d_hit_v, 0, need * 4, ctx->dev[0].stream));
+    CK(cudaStreamSynchronize(ctx->dev[0].stream));
+    return 0;
+}
+
+void fill_camera(const cuda_trace_ctx *ctx, const cuda_trace_frame *f, const FrameKind& kind, TraceParams& p)
+{
+    for (int r = 0; r < 3; r++)
+    {
+        for (int c = 0; c < 3; c++)
+            p.cam.m[r][c] = f->cam_mat[r * 4 + c];
+        // perspective: origin = Transf4x4(Vec3f(0)) (camera.h:43, lin_alg.h:518-535), all four terms kept
+        // (a -0 translation comes out as +0); orthographic: the raw row, used per ray
+        const float zero = 0.0f, m3 = f->cam_mat[12 + r];
+        p.cam.origin[r] = kind.ortho ? m3 : zero * f->cam_mat[0 + r] + zero * f->cam_mat[4 + r] + zero * f->cam_mat[8 + r] + m3;
+    }
+    p.cam.ortho = kind.ortho ? 1u : 0u;
+    {
+        // camera.h:28-31: const float width = width_or_hfov, height = float(width) / aspect; half = x / 2.0
+        const float ow = f->fov_xs, oh = ow / f->aspect;
+        p.cam.ortho_half_w = (float) ((double) ow / 2.0);
+        p.cam.ortho_half_h = (float) ((double) oh / 2.0);
+    }
+    p.shade_mode = kind.shade_mode;
+    p.cam.fov_xs = f->fov_xs;
+    p.cam.aspect = f->aspect;
+    p.cam.width_f = (float) f->width;
+    p.cam.height_f = (float) f->height;
+    // frame constants of the range-check-free divisions (rt_device.cuh): valid while every operand and
+    // quotient of generate_ray and of the DDA set-up is an ordinary normal number
+    p.cam.inv_width = 1.0f / p.cam.width_f;
+    p.cam.inv_height = 1.0f / p.cam.height_f;
+    p.cam.inv_aspect = 1.0f / f->aspect;
+    const auto ordinary = [](float x) { return std::fabs(x) >= 0x1p-20f && std::fabs(x) <= 0x1p20f; };
+    p.cam.fast_math = (ctx->fast_math && ordinary(f->fov_xs) && ordinary(f->aspect) && ordinary(ctx->desc.cell_wdh) &&
+                       f->width <= (1u << 20) && f->height <= (1u << 20)) ? 1u : 0u;
+    p.width = f->width;
+    p.height = f->height;
+    p.spp = f->spp;
+    p.gamma = (f->flags & CUDA_TRACE_FLAG_GAMMA) ? 1u : 0u;
+    const float one[2] = { 1.0f, 1.0f }, minus_one[2] = { -1.0f, -1.0f };
+    std::memcpy(&p.pk_one, one, sizeof(p.pk_one));
+    std::memcpy(&p.pk_minus_one, minus_one, sizeof(p.pk_minus_one));
+}
+
+// Where the padded occupancy map is read from (warp_trace.cuh): one byte per cell in shared memory when that leaves
+// room (<= 160 KB), else bits in shared memory, else bits through L1.  Tiny frames skip the per-CTA staging.
+// CTA size: one 1024-thread CTA per SM measured best on every config (32 warps share one staged occupancy map and
+// pull neighbouring strips, which keeps the triangle records of that screen region in L1); small frames use
+// smaller CTAs so that every SM gets work.
+int choose_cta(const cuda_trace_ctx *ctx, const DeviceState& d, const cuda_trace_frame *f, uint64_t strips_here, TraceParams& p)
+{
+    int threads = 1024;
+    const uint64_t pcells = (uint64_t) (ctx->desc.dim[0] + 2) * (ctx->desc.dim[1] + 2) * (ctx->desc.dim[2] + 2);
+    const uint64_t bit_words = (pcells + 31) / 32, byte_words = (pcells + 3) / 4;
+    const uint64_t rays = (uint64_t) f->width * f->height * f->spp;
+    const size_t smp_bytes = sizeof(float2) * f->spp;
+    while (threads > 64 && strips_here < (uint64_t) d.sm_count * (threads / 32))
+        threads /= 2;
+    p.occ_mode = kOccGlobalBits;
+    p.occ_smem_words = 0;
+    if (ctx->occ_in_smem && rays >= (4u << 20) && threads == 1024)
+    {
+        if (byte_words * 4 + smp_bytes <= 160 * 1024)
+        {
+            p.occ_mode = kOccSmemBytes;
+            p.occ_smem_words = (uint32_t) byte_words;
+        }
+        else if (bit_words * 4 + smp_bytes <= 160 * 1024)
+        {
+            p.occ_mode = kOccSmemBits;
+            p.occ_smem_words = (uint32_t) bit_words;
+        }
+    }
+    const int m = ctx->tune.occ_mode;
+    if (m == kOccGlobalBits) { p.occ_mode = kOccGlobalBits; p.occ_smem_words = 0; }
+    if (m == kOccSmemBits && bit_words * 4 + smp_bytes <= 200 * 1024) { p.occ_mode = kOccSmemBits; p.occ_smem_words = (uint32_t) bit_words; }
+    if (m == kOccSmemBytes && byte_words * 4 + smp_bytes <= 200 * 1024) { p.occ_mode = kOccSmemBytes; p.occ_smem_words = (uint32_t) byte_words; }
+    if (ctx->tune.threads)
+        threads = ctx->tune.threads;
+    // |det| <= |e1| |e2| |d| <= 3 extent^2: below 1e14 the reciprocal's fast path is always valid
+    float extent = 0.0f;
+    for (int k = 0; k < 3; k++)
+        extent = std::max(extent, ctx->desc.aabb_max[k] - ctx->desc.aabb_min[k]);
+    p.rcp_guard = (extent < 1.0e14f) ? 0u : 1u;
+    return threads;
+}
+
+// Cost order from the previous frame (schedule.cu), valid only if that frame had the same layout and shard.
+// Worth its ~1 % instrumentation cost when the frame is sharded or small (the tail of expensive strips is then a
+// large part of the launch); RTM_COST_ORDER=0/1 forces it
+int prepare_cost_order(cuda_trace_ctx *ctx, DeviceState& d, const cuda_trace_frame *f, TraceParams& p)
+{
+    const FramePlan& pl = ctx->plan;
+    const uint32_t shard_strips = p.shard_strips;
+    p.fetch_order = nullptr;
+    p.visit_cycles = nullptr;
+    p.visit_total = nullptr;
+    const bool want_order = (ctx->cost_order_forced >= 0 ? ctx->cost_order_forced != 0
+                            : (p.shard_world > 1 || (uint64_t) f->width * f->height * f->spp < (64ull << 20))) &&
+                            shard_strips <= kVisitStripMask;
+    if (!want_order || shard_strips == 0)
+    {
+        d.order_valid = false;
+        return 0;
+    }
+    if (d.order_pending)
+    {
+        CK(cudaStreamWaitEvent(d.stream, d.ev_order, 0)); // the order this frame follows / the buffers it reuses
+        d.order_pending = false;
+    }
+    if (d.order_cap < shard_strips)
+    {
+        CK(cudaStreamSynchronize(d.order_stream));
+        cudaFree(d.d_strip_cycles); cudaFree(d.d_fetch_order); cudaFree(d.d_order_scratch); cudaFree(d.d_visit_cycles);
+        d.d_strip_cycles = d.d_fetch_order = d.d_order_scratch = d.d_visit_cycles = nullptr;
+        d.order_cap = 0;
+        d.order_valid = false;
+        CK(cudaMalloc(&d.d_strip_cycles, sizeof(uint32_t) * shard_strips));
+        CK(cudaMalloc(&d.d_fetch_order, sizeof(uint32_t) * strip_order_capacity(shard_strips, 4)));
+        CK(cudaMalloc(&d.d_visit_cycles, sizeof(uint32_t) * strip_order_capacity(shard_strips, 4)));
+        CK(cudaMalloc(&d.d_order_scratch, sizeof(uint32_t) * strip_order_scratch_words(shard_strips)));
+        if (!d.d_cost_sum)
+            CK(cudaMalloc(&d.d_cost_sum, sizeof(unsigned long long)));
+        if (!d.d_visit_total)
+            CK(cudaMalloc(&d.d_visit_total, sizeof(uint32_t)));
+        d.order_cap = shard_strips;
+    }
+    const std::vector<uint64_t> sig = { pl.serial, p.shard_rank, p.shard_world, p.shard_chunk, shard_strips };
+    if (d.order_valid && sig == d.order_signature)
+        p.fetch_order = d.d_fetch_order;
+    p.visit_total = d.d_visit_total;
+    d.order_signature = sig;
+    d.order_strips = shard_strips;
+    p.visit_cycles = d.d_visit_cycles;
+    CK(cudaMemsetAsync(d.d_visit_cycles, 0, sizeof(uint32_t) * strip_order_capacity(shard_strips, pl.split_parts), d.stream));
+    return 0;
+}
+
+// Everything device `i` of the context does for this frame
+int launch_on_device(cuda_trace_ctx *ctx, uint32_t i, const cuda_trace_frame *f, const FrameKind& kind, bool use_bands, uint32_t seq)
+{
+    DeviceState& d = ctx->dev[i];
+    const FramePlan& pl = ctx->plan;
+    const uint32_t n_dev = (uint32_t) ctx->dev.size(), n_tiles = (uint32_t) pl.rects.size();
+    CK(cudaSetDevice(d.ordinal));
+    if (d.smp_cap < f->spp)
+    {
+        cudaFree(d.d_smp);
+        d.d_smp = nullptr;
+        CK(cudaMalloc(&d.d_smp, sizeof(float2) * f->spp));
+        d.smp_cap = f->spp;
+        d.smp_valid_spp = 0;
+    }
+    if (d.smp_valid_spp != f->spp)
+    {
+        launch_sample_table(d.d_smp, f->spp, d.stream); // K2
+        ctx->launches++;
+        d.smp_valid_spp = f->spp;
+    }
+    if (d.tile_cap < n_tiles + 1)
+    {
+        cudaFree(d.d_tile_rects); cudaFree(d.d_tile_prefix);
+        d.d_tile_rects = nullptr; d.d_tile_prefix = nullptr;
+        d.tile_cap = std::max<uint32_t>(n_tiles + 1, 128);
+        d.layout_serial = 0;
+        CK(cudaMalloc(&d.d_tile_rects, sizeof(uint4) * d.tile_cap));
+        CK(cudaMalloc(&d.d_tile_prefix, sizeof(uint32_t) * d.tile_cap));
+    }
+    // the tile list usually repeats from frame to frame: upload it only when it changed (the plan owns the host
+    // arrays, so the asynchronous copies need no synchronisation before returning)
+    if (d.layout_serial != pl.serial)
+    {
+        d.layout_serial = 0;
+        if (n_tiles)
+            CK(cudaMemcpyAsync(d.d_tile_rects, pl.rects.data(), sizeof(uint4) * n_tiles, cudaMemcpyHostToDevice, d.stream));
+        CK(cudaMemcpyAsync(d.d_tile_prefix, pl.prefix.data(), sizeof(uint32_t) * (n_tiles + 1), cudaMemcpyHostToDevice, d.stream));
+        CK(cudaStreamSynchronize(d.stream)); // pageable source: consumed before the plan can be replaced
+        d.layout_serial = pl.serial;
+    }
+    // strip counter + this GPU's per-band piece counts (the cancel word behind them is never cleared)
+    CK(cudaMemsetAsync(d.d_strip_counter, 0, (32 + kMaxBands) * sizeof(uint32_t), d.stream));
+    if (ctx->counting)
+        CK(cudaMemsetAsync(d.d_counters, 0, sizeof(Counters), d.stream));
+
+    TraceParams p;
+    p.grid = grid_dev(ctx, d);
+    fill_camera(ctx, f, kind, p);
+    p.smp = d.d_smp;
+    p.tile_rects = d.d_tile_rects;
+    p.tile_strip_prefix = d.d_tile_prefix;
+    p.n_tiles = n_tiles;
+    p.strip_w = pl.strip_w;
+    p.strip_h = pl.strip_h;
+    p.split_parts = pl.split_parts;
+    p.total_strips = (uint32_t) pl.total;
+    // strips are interleaved first over the processes (shard), then over this context's devices
+    p.shard_world = ctx->shard_world * n_dev;
+    p.shard_rank = ctx->shard_rank * n_dev + i;
+    p.shard_chunk = ctx->shard_chunk;
+    p.strip_counter = d.d_strip_counter;
+    p.cancel = d.d_cancel;
+    p.cancel_seen = d.d_cancel_seen;
+    p.frame_seq = seq;
+    p.framebuffer = ctx->d_fb;
+    p.band_done = use_bands ? band_counters(ctx) : nullptr;
+    p.band_rows = ctx->band_rows;
+    p.band_local = ctx->two_level ? d.d_strip_counter + 32 : nullptr; // own cache line
+    std::memset(p.band_share, 0, sizeof(p.band_share));
+    if (use_bands)
+        std::memcpy(p.band_share, ctx->band_share[p.shard_rank].data(), sizeof(p.band_share));
+    // Who reads the band counters and the pixels behind them?  Another GPU's memory or a copy engine: neither is
+    // inside this GPU's .gpu scope, so the publishing release is at system scope.  (.gpu only for RTM_FORCE_BANDS
+    // runs without a reader.)
+    p.band_scope_sys = ctx->two_level ? 1u : 0u;
+    p.hit_tri = kind.keep_hits ? ctx->d_hit_tri : nullptr;
+    p.hit_t = kind.keep_hits ? ctx->d_hit_t : nullptr;
+    p.hit_u = kind.keep_hits ? ctx->d_hit_u : nullptr;
+    p.hit_v = kind.keep_hits ? ctx->d_hit_v : nullptr;
+    p.counters = d.d_counters;
+
+    const uint64_t strips_here = (pl.total + p.shard_world - 1) / p.shard_world;
+    const int threads = choose_cta(ctx, d, f, strips_here, p);
+    {
+        const uint64_t chunks_total = (pl.total + p.shard_chunk - 1) / p.shard_chunk;
+        const uint64_t my_chunks = (chunks_total + p.shard_world - 1) / p.shard_world;
+        p.shard_strips = (uint32_t) (my_chunks * p.shard_chunk); // (< 2^32: checked by the caller)
+    }
+    int rc = prepare_cost_order(ctx, d, f, p);
+    if (rc)
+        return rc;
+
+    // Moeller-Trumbore on origin-relative records when the per-camera pre-pass is negligible (a few M cell
+    // references: < 0.1 ms) -- not for the instrumented (counting) kernels; RTM_REL_RECORDS=0 switches it off;
+    // nor for small frames: measured +5..9 % on 33 M rays and more (4K and 1080p at 16 spp), -1 % on the 8 M rays
+    // of 1080p / 4 spp, -10 % on 512^2 / 1 spp, which is launch- and cold-miss-bound (the records are 112 B, not 80)
+    const bool rel_fits = ctx->desc.num_refs <= (4ull << 20) &&
+                          ((uint64_t) f->width * f->height * f->spp >= (16ull << 20) || ctx->rel_records_forced);
+    const uint32_t kvariant = kind.alternates ? (uint32_t) kVariantMTAlt + f->variant
+                              : (f->variant == kVariantMT && !kind.count_inst && ctx->rel_records && rel_fits)
+                                  ? (uint32_t) kVariantMTRel : f->variant;
+    const size_t smem_bytes = trace_tiles_smem_bytes(f->spp, p.occ_smem_words);
+    const std::vector<long long> okey = { (long long) kvariant, kind.keep_hits, kind.count_inst, (long long) p.occ_mode, threads,
+                                          (long long) smem_bytes };
+    if (okey != d.occupancy_key)
+    {
+        d.blocks_per_sm = std::max(1, trace_tiles_max_blocks_per_sm(kvariant, kind.keep_hits, kind.count_inst, (int) p.occ_mode,
+                                                                    threads, smem_bytes));
+        d.occupancy_key = okey;
+    }
+    const uint64_t want = (strips_here + (threads / 32) - 1) / (threads / 32);
+    const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) d.sm_count * d.blocks_per_sm, want));
+    {
+        // How many finished strips a warp collects before it publishes them to the band counters: the fence
+        // costs ~1 us, but a held-back strip delays its band's read-back -- at most 1/16 of a warp's share
+        // of the frame (8 strips for a whole 4K frame on one GPU, every strip for an eighth of it)
+        const uint64_t warps = (uint64_t) blocks * (threads / 32);
+        uint64_t hold = std::min<uint64_t>(8, std::max<uint64_t>(1, strips_here / std::max<uint64_t>(1, warps * 16)));
+        if (ctx->tune.band_flush)
+            hold = (uint64_t) ctx->tune.band_flush;
+        p.band_flush_units = (uint32_t) hold * pl.split_parts;
+    }
+    if (i == 0)
+        ctx->t_launching_ms = ms_since(ctx->t_enter);
+    CK(cudaEventRecord(d.ev_begin, d.stream));
+    if (kvariant == kVariantMTRel && pl.total)
+    {
+        // records relative to this frame's camera position: rebuilt (inside the timed region) when it moved
+        if (!d.d_pair_recs_rel)
+            CK(cudaMalloc(&d.d_pair_recs_rel, std::max<uint64_t>(ctx->num_pairs, 1) * 7 * sizeof(float4)));
+        if (!d.rel_valid || std::memcmp(d.rel_origin, p.cam.origin, sizeof(d.rel_origin)) != 0)
+        {
+            launch_origin_relative_pairs(d.d_pair_recs, std::max<uint64_t>(ctx->num_pairs, 1), p.cam.origin, d.d_pair_recs_rel, d.stream);
+            ctx->launches++;
+            std::memcpy(d.rel_origin, p.cam.origin, sizeof(d.rel_origin));
+            d.rel_valid = true;
+        }
+        p.grid.pair_recs_rel = d.d_pair_recs_rel;
+    }
+    if (pl.total)
+    {
+        launch_trace_tiles(p, kvariant, kind.keep_hits, kind.count_inst, blocks, threads, d.stream);
+        ctx->launches++;
+    }
+    if (i == 0)
+        ctx->t_launched_ms = ms_since(ctx->t_enter);
+    CK(cudaEventRecord(d.ev_end, d.stream));
+    d.launched_seq = seq;
+    d.frame_pending = true;
+    d.order_followup = p.visit_cycles && pl.total;
+    d.order_followup_used = p.fetch_order != nullptr;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// this frame's strip costs -> next frame's visiting order (own stream, behind the trace kernel; enqueued after the
+// band copies so that it does not delay them)
+int enqueue_order_followup(cuda_trace_ctx *ctx, DeviceState& d)
+{
+    if (!d.order_followup)
+        return 0;
+    d.order_followup = false;
+    CK(cudaSetDevice(d.ordinal));
+    CK(cudaEventRecord(d.ev_traced, d.stream));
+    CK(cudaStreamWaitEvent(d.order_stream, d.ev_traced, 0));
+    launch_build_strip_order(d.d_visit_cycles, d.order_followup_used, d.d_strip_cycles, d.order_strips, ctx->plan.split_parts,
+                             d.d_cost_sum, d.d_order_scratch, d.d_visit_total, d.d_fetch_order, d.order_stream);
+    CK(cudaEventRecord(d.ev_order, d.order_stream));
+    d.order_pending = true;
+    ctx->launches += 5;
+    d.order_valid = true;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Copy stream of device 0: wait for each row band's completion count, ship the band to the host buffer
+int enqueue_band_copies(cuda_trace_ctx *ctx, const cuda_trace_frame *f, uint32_t *host_bgra, const uint32_t *expected)
+{
+    DeviceState& d0 = ctx->dev[0];
+    CK(cudaSetDevice(d0.ordinal));
+    uint32_t *counters = band_counters(ctx);
+    for (uint32_t b = 0; b < ctx->n_bands; b++)
+    {
+        const uint32_t y0 = b * ctx->band_rows, y1 = std::min(f->height, y0 + ctx->band_rows);
+        if (ctx->wait_value32(d0.copy_stream, (unsigned long long) (uintptr_t) (counters + b), expected[b],
+                              0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
+            return fail(ctx, CUDA_TRACE_ERR_CUDA, "cuStreamWaitValue32 failed");
+        CK(cudaMemcpyAsync(host_bgra + (size_t) y0 * f->width, ctx->d_fb + (size_t) y0 * f->width,
+                           (size_t) (y1 - y0) * f->width * sizeof(uint32_t), cudaMemcpyDeviceToHost, d0.copy_stream));
+    }
+    ctx->copy_pending = true;
+    return 0;
+}
+
+} // namespace
 
 static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const cuda_trace_tile_rect *tiles,
                             uint32_t n_tiles, uint32_t *host_bgra)
 {
     if (!ctx || !f || (!tiles && n_tiles))
         return CUDA_TRACE_ERR_ARG;
-    if (!ctx->have_scene)
-        return fail(ctx, CUDA_TRACE_ERR_NO_SCENE, "trace_tiles: upload a scene first");
-    if (f->width == 0 || f->height == 0 || f->spp == 0 || f->variant > 1)
-        return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: bad frame description");
-    if ((uint64_t) f->width * f->height >= (1ull << 32))
-        return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: frame too large");
-    int rc = cuda_trace_sync(ctx); // one frame in flight per context
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
+    FrameKind kind;
+    int rc = check_frame_args(ctx, f, tiles, n_tiles, kind);
+    if (rc)
+        return rc;
+    rc = cuda_trace_sync(ctx); // one frame in flight per context
     if (rc && rc != CUDA_TRACE_ERR_CANCELLED)
         return rc;
-
-    // strips per tile (strip_w x strip_h pixel blocks, clipped to the tile)
-    uint32_t strip_w, strip_h;
-    strip_size_for_spp(f->spp, (uint64_t) f->width * f->height * f->spp, strip_w, strip_h);
-    if (const char *e = std::getenv("RTM_STRIP_PIXELS")) // tuning override (experiments only): 2,4,8,16,32
+    if ((rc = update_plan(ctx, f, tiles, n_tiles)))
+        return rc;
+    const FramePlan& pl = ctx->plan;
+    const uint32_t n_dev = (uint32_t) ctx->dev.size();
     {
-        const uint32_t px = (uint32_t) std::atoi(e);
-        if (px == 2 || px == 4 || px == 8 || px == 16 || px == 32)
-        {
-            strip_w = px >= 32 ? 8 : (px >= 8 ? 4 : 2);
-            strip_h = px >= 16 ? 4 : (px >= 4 ? 2 : 1);
-        }
-    }
-    uint32_t split_parts = strip_split_parts(strip_w, strip_h, f->spp);
-    if (const char *e = std::getenv("RTM_SPLIT_PARTS")) // tuning override (experiments only): 1 = never split
-        if (std::atoi(e) == 1 || (std::atoi(e) == 2 && split_parts >= 2))
-            split_parts = (uint32_t) std::atoi(e);
-    std::vector<uint4> rects(n_tiles);
-    std::vector<uint32_t> prefix(n_tiles + 1, 0);
-    uint64_t total = 0;
-    for (uint32_t i = 0; i < n_tiles; i++)
-    {
-        const cuda_trace_tile_rect& t = tiles[i];
-        if (t.x0 > t.x1 || t.y0 > t.y1 || t.x1 > f->width || t.y1 > f->height)
-            return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: tile " + std::to_string(i) + " outside the frame");
-        rects[i] = make_uint4(t.x0, t.y0, t.x1, t.y1);
-        prefix[i] = (uint32_t) total;
-        total += (uint64_t) ((t.x1 - t.x0 + strip_w - 1) / strip_w) * ((t.y1 - t.y0 + strip_h - 1) / strip_h);
-        if (total >= (1ull << 32))
+        const uint64_t world = (uint64_t) ctx->shard_world * n_dev;
+        const uint64_t chunks_total = (pl.total + ctx->shard_chunk - 1) / ctx->shard_chunk;
+        if ((chunks_total + world - 1) / world * ctx->shard_chunk >= (1ull << 32))
             return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: too many strips");
     }
-    prefix[n_tiles] = (uint32_t) total;
-    std::vector<uint32_t> layout_sig = { n_tiles, strip_w, strip_h };
-    for (uint32_t i = 0; i < n_tiles; i++)
-    {
-        layout_sig.push_back(rects[i].x); layout_sig.push_back(rects[i].y);
-        layout_sig.push_back(rects[i].z); layout_sig.push_back(rects[i].w);
-    }
-
+    if (ctx->band_dirty && (rc = resync_band_counters(ctx)))
+        return rc;
     if ((rc = ensure_framebuffer(ctx, f->width, f->height)))
         return rc;
-    const bool keep_hits = (f->flags & CUDA_TRACE_FLAG_KEEP_HITS) != 0;
-    if (keep_hits)
+    if (kind.keep_hits)
     {
-        const uint64_t need = (uint64_t) f->width * f->height * f->spp;
-        if (need > ctx->hit_cap)
-        {
-            CK(cudaSetDevice(ctx->dev[0].ordinal));
-            cudaFree(ctx->d_hit_tri); cudaFree(ctx->d_hit_t); cudaFree(ctx->d_hit_u); cudaFree(ctx->d_hit_v);
-            ctx->d_hit_tri = nullptr; ctx->d_hit_t = ctx->d_hit_u = ctx->d_hit_v = nullptr;
-            ctx->hit_cap = 0;
-            CK(cudaMalloc(&ctx->d_hit_tri, need * 4));
-            CK(cudaMalloc(&ctx->d_hit_t, need * 4));
-            CK(cudaMalloc(&ctx->d_hit_u, need * 4));
-            CK(cudaMalloc(&ctx->d_hit_v, need * 4));
-            ctx->hit_cap = need;
-        }
-        ctx->hit_count = need;
-        CK(cudaSetDevice(ctx->dev[0].ordinal));
-        // samples outside the requested tiles read as "miss"
-        CK(cudaMemsetAsync(ctx->d_hit_tri, 0xFF, need * 4, ctx->dev[0].stream));
-        CK(cudaMemsetAsync(ctx->d_hit_t, 0, need * 4, ctx->dev[0].stream));
-        CK(cudaMemsetAsync(ctx->d_hit_u, 0, need * 4, ctx->dev[0].stream));
-        CK(cudaMemsetAsync(ctx->d_hit_v, 0, need * 4, ctx->dev[0].stream));
-        CK(cudaStreamSynchronize(ctx->dev[0].stream));
+        if ((rc = ensure_hit_buffers(ctx, f)))
+            return rc;
     }
     else
         ctx->hit_count = 0;
-    if (ctx->dev.size() > 1)
+    if (n_dev > 1)
         CK(cudaStreamSynchronize(ctx->dev[0].stream)); // framebuffer (re)allocation visible to peers
 
     ctx->frame = *f;
     ctx->tiles.assign(tiles, tiles + n_tiles);
     ctx->frame_valid = true;
 
-    // Overlapped read-back: row bands whose strips are all finished are copied to the host while
-    // the rest of the frame is still being traced.  Needs the whole frame covered by the tile list
-    // and, when the frame is sharded over processes, every rank signalling (set_shard_signals).
-    uint64_t covered = 0;
-    for (uint32_t i = 0; i < n_tiles; i++)
-        covered += (uint64_t) (tiles[i].x1 - tiles[i].x0) * (tiles[i].y1 - tiles[i].y0);
-    const bool can_overlap = host_bgra && ctx->overlap_d2h && ctx->wait_value32 && !ctx->fb_imported && total > 0 &&
-                             covered >= (uint64_t) f->width * f->height && (ctx->shard_world == 1 || ctx->shard_signals);
-    const bool use_bands = ctx->shard_signals || can_overlap || std::getenv("RTM_FORCE_BANDS") != nullptr;
+    // Overlapped read-back: row bands whose strips are all finished are copied to the host while the rest of the
+    // frame is still being traced.  Needs the whole frame covered by the tile list (exactly: a partition) and, when
+    // the frame is sharded over processes, every rank signalling (set_shard_signals).
+    const bool can_overlap = host_bgra && ctx->overlap_d2h && ctx->wait_value32 && !ctx->fb_imported && pl.total > 0 &&
+                             pl.covers_frame && (ctx->shard_world == 1 || ctx->shard_signals);
+    const bool use_bands = ctx->shard_signals || can_overlap || ctx->tune.force_bands;
+    ctx->two_level = ctx->shard_world * n_dev > 1 || ctx->fb_imported || ctx->shard_signals || can_overlap;
     if (use_bands)
-    {
-        band_layout(f->width, f->height, strip_h, ctx->band_rows, ctx->n_bands);
-        const uint32_t participants = ctx->shard_world * (uint32_t) ctx->dev.size();
-        // one GPU storing into its own framebuffer counts pieces straight into the band counters (a release at
-        // GPU scope is cheap); several GPUs count locally first and bump the shared counter once per band
-        const uint32_t two_level = (participants > 1 || ctx->fb_imported) ? 1u : 0u;
-        std::vector<uint32_t> bsig = { f->width, f->height, strip_w, strip_h, n_tiles, ctx->band_rows, split_parts,
-                                       participants, ctx->shard_chunk, two_level };
-        for (uint32_t k = 0; k < n_tiles; k++)
-        {
-            bsig.push_back(rects[k].x ^ (rects[k].z << 16));
-            bsig.push_back(rects[k].y ^ (rects[k].w << 16));
-        }
-        if (bsig != ctx->band_inc_sig)
-        {
-            band_shares(rects, prefix, strip_w, strip_h, ctx->band_rows, split_parts, ctx->shard_chunk, participants,
-                        ctx->band_share, ctx->band_inc);
-            if (!two_level)
-                for (int b = 0; b < kMaxBands; b++)
-                    ctx->band_inc[b] = ctx->band_share[0][b];
-            ctx->band_inc_sig = bsig;
-        }
-        for (uint32_t b = 0; b < ctx->n_bands; b++)
-            ctx->band_expected[b] += ctx->band_inc[b]; // counters are monotone across frames (wrap-safe compare)
-    }
+        plan_band_counts(ctx);
 
-    const uint32_t n_dev = (uint32_t) ctx->dev.size();
+    // From here on the device counters move: should anything fail before every device's kernel is enqueued, the
+    // totals are re-read from the device at the next call instead of being trusted
+    const uint32_t seq = ++ctx->frame_seq;
+    ctx->band_dirty = use_bands;
     ctx->t_prepared_ms = ms_since(ctx->t_enter);
+    uint32_t expected[kMaxBands];
+    for (int b = 0; b < kMaxBands; b++)
+        expected[b] = ctx->band_expected[b] + (use_bands && (uint32_t) b < ctx->n_bands ? ctx->band_inc[b] : 0u); // monotone across frames (wrap-safe compare)
+    // device 0 first, then its band copies, then the other devices: the copy stream is armed while the kernels start
     for (uint32_t i = 0; i < n_dev; i++)
     {
-        DeviceState& d = ctx->dev[i];
-        CK(cudaSetDevice(d.ordinal));
-        if (d.smp_cap < f->spp)
-        {
-            cudaFree(d.d_smp);
-            d.d_smp = nullptr;
-            CK(cudaMalloc(&d.d_smp, sizeof(float2) * f->spp));
-            d.smp_cap = f->spp;
-            d.smp_valid_spp = 0;
-        }
-        if (d.smp_valid_spp != f->spp)
-        {
-            launch_sample_table(d.d_smp, f->spp, d.stream); // K2
-            ctx->launches++;
-            d.smp_valid_spp = f->spp;
-        }
-        if (d.tile_cap < n_tiles + 1)
-        {
-            cudaFree(d.d_tile_rects); cudaFree(d.d_tile_prefix);
-            d.d_tile_rects = nullptr; d.d_tile_prefix = nullptr;
-            d.tile_cap = std::max<uint32_t>(n_tiles + 1, 128);
-            d.layout_sig.clear();
-            CK(cudaMalloc(&d.d_tile_rects, sizeof(uint4) * d.tile_cap));
-            CK(cudaMalloc(&d.d_tile_prefix, sizeof(uint32_t) * d.tile_cap));
-        }
-        // the tile list usually repeats from frame to frame: upload it only when it changed
-        const bool new_layout = d.layout_sig != layout_sig;
-        if (new_layout)
-        {
-            d.layout_sig.clear();
-            if (n_tiles)
-                CK(cudaMemcpyAsync(d.d_tile_rects, rects.data(), sizeof(uint4) * n_tiles, cudaMemcpyHostToDevice, d.stream));
-            CK(cudaMemcpyAsync(d.d_tile_prefix, prefix.data(), sizeof(uint32_t) * (n_tiles + 1), cudaMemcpyHostToDevice,
-                               d.stream));
-        }
-        // strip counter + cancel flag + this GPU's per-band piece counts
-        CK(cudaMemsetAsync(d.d_strip_counter, 0, (32 + kMaxBands) * sizeof(uint32_t), d.stream));
-        if (ctx->counting)
-            CK(cudaMemsetAsync(d.d_counters, 0, sizeof(Counters), d.stream));
-        if (new_layout)
-        {
-            // rects / prefix are pageable host vectors: the async copies above have consumed them
-            // only once the stream reaches them, so wait before they go out of scope
-            CK(cudaStreamSynchronize(d.stream));
-            d.layout_sig = layout_sig;
-        }
-
-        TraceParams p;
-        p.grid = grid_dev(ctx, d);
-        const bool ortho = (f->flags & CUDA_TRACE_FLAG_ORTHO) != 0;
-        for (int r = 0; r < 3; r++)
-        {
-            for (int c = 0; c < 3; c++)
-                p.cam.m[r][c] = f->cam_mat[r * 4 + c];
-            // perspective: origin = Transf4x4(Vec3f(0)) (camera.h:43, lin_alg.h:518-535), all four terms kept
-            // (a -0 translation comes out as +0); orthographic: the raw row, used per ray
-            const float zero = 0.0f, m3 = f->cam_mat[12 + r];
-            p.cam.origin[r] = ortho ? m3 : zero * f->cam_mat[0 + r] + zero * f->cam_mat[4 + r] + zero * f->cam_mat[8 + r] + m3;
-        }
-        p.cam.ortho = ortho ? 1u : 0u;
-        {
-            // camera.h:28-31: const float width = width_or_hfov, height = float(width) / aspect; half = x / 2.0
-            const float ow = f->fov_xs, oh = ow / f->aspect;
-            p.cam.ortho_half_w = (float) ((double) ow / 2.0);
-            p.cam.ortho_half_h = (float) ((double) oh / 2.0);
-        }
-        p.shade_mode = (f->flags & CUDA_TRACE_FLAG_SHADE_FACE_NORMAL) ? 1u : ((f->flags & CUDA_TRACE_FLAG_SHADE_DEPTH) ? 2u : 0u);
-        p.cam.fov_xs = f->fov_xs;
-        p.cam.aspect = f->aspect;
-        p.cam.width_f = (float) f->width;
-        p.cam.height_f = (float) f->height;
-        {
-            // frame constants of the range-check-free divisions (rt_device.cuh): valid while every operand and
-            // quotient of generate_ray and of the DDA set-up is an ordinary normal number
-            p.cam.inv_width = 1.0f / p.cam.width_f;
-            p.cam.inv_height = 1.0f / p.cam.height_f;
-            p.cam.inv_aspect = 1.0f / f->aspect;
-            const auto ordinary = [](float x) { return std::fabs(x) >= 0x1p-20f && std::fabs(x) <= 0x1p20f; };
-            p.cam.fast_math = (ctx->fast_math && ordinary(f->fov_xs) && ordinary(f->aspect) && ordinary(ctx->desc.cell_wdh) &&
-                               f->width <= (1u << 20) && f->height <= (1u << 20)) ? 1u : 0u;
-        }
-        p.width = f->width;
-        p.height = f->height;
-        p.spp = f->spp;
-        p.gamma = (f->flags & CUDA_TRACE_FLAG_GAMMA) ? 1u : 0u;
-        p.smp = d.d_smp;
-        // Where the padded occupancy map is read from (warp_trace.cuh): one byte per cell in shared
-        // memory when that leaves room for two 512-thread CTAs (or one 1024-thread CTA) per SM,
-        // else bits in shared memory, else bits through L1.  Tiny frames skip the per-CTA staging.
-        // CTA size: one 1024-thread CTA per SM measured best on every config (32 warps share one
-        // staged occupancy map and pull neighbouring strips, which keeps the triangle records of
-        // that screen region in L1); small frames use smaller CTAs so that every SM gets work.
-        int threads = 1024;
-        {
-            const uint64_t pcells = (uint64_t) (ctx->desc.dim[0] + 2) * (ctx->desc.dim[1] + 2) * (ctx->desc.dim[2] + 2);
-            const uint64_t bit_words = (pcells + 31) / 32, byte_words = (pcells + 3) / 4;
-            const uint64_t rays = (uint64_t) f->width * f->height * f->spp;
-            const size_t smp_bytes = sizeof(float2) * f->spp;
-            const uint64_t strips_here = (total + (uint64_t) ctx->shard_world * n_dev - 1) / ((uint64_t) ctx->shard_world * n_dev);
-            while (threads > 64 && strips_here < (uint64_t) d.sm_count * (threads / 32))
-                threads /= 2;
-            p.occ_mode = kOccGlobalBits;
-            p.occ_smem_words = 0;
-            if (ctx->occ_in_smem && rays >= (4u << 20) && threads == 1024)
-            {
-                if (byte_words * 4 + smp_bytes <= 160 * 1024)
-                {
-                    p.occ_mode = kOccSmemBytes;
-                    p.occ_smem_words = (uint32_t) byte_words;
-                }
-                else if (bit_words * 4 + smp_bytes <= 160 * 1024)
-                {
-                    p.occ_mode = kOccSmemBits;
-                    p.occ_smem_words = (uint32_t) bit_words;
-                }
-            }
-            // tuning overrides (experiments only): RTM_OCC_MODE = 0 | 1 | 2, RTM_THREADS = CTA size
-            if (const char *e = std::getenv("RTM_OCC_MODE"))
-            {
-                const int m = std::atoi(e);
-                if (m == kOccGlobalBits) { p.occ_mode = kOccGlobalBits; p.occ_smem_words = 0; }
-                if (m == kOccSmemBits && bit_words * 4 + smp_bytes <= 200 * 1024) { p.occ_mode = kOccSmemBits; p.occ_smem_words = (uint32_t) bit_words; }
-                if (m == kOccSmemBytes && byte_words * 4 + smp_bytes <= 200 * 1024) { p.occ_mode = kOccSmemBytes; p.occ_smem_words = (uint32_t) byte_words; }
-            }
-            if (const char *e = std::getenv("RTM_THREADS"))
-            {
-                const int t = std::atoi(e);
-                if (t >= 32 && t <= 1024 && t % 32 == 0)
-                    threads = t;
-            }
-            // |det| <= |e1| |e2| |d| <= 3 extent^2: below 1e14 the reciprocal's fast path is always valid
-            float extent = 0.0f;
-            for (int k = 0; k < 3; k++)
-                extent = std::max(extent, ctx->desc.aabb_max[k] - ctx->desc.aabb_min[k]);
-            p.rcp_guard = (extent < 1.0e14f) ? 0u : 1u;
-        }
-        p.tile_rects = d.d_tile_rects;
-        p.tile_strip_prefix = d.d_tile_prefix;
-        p.n_tiles = n_tiles;
-        p.strip_w = strip_w;
-        p.strip_h = strip_h;
-        p.split_parts = split_parts;
-        p.visit_total = nullptr;
-        p.total_strips = (uint32_t) total;
-        // strips are interleaved first over the processes (shard), then over this context's devices
-        p.shard_world = ctx->shard_world * n_dev;
-        p.shard_rank = ctx->shard_rank * n_dev + i;
-        p.shard_chunk = ctx->shard_chunk;
-        p.strip_counter = d.d_strip_counter;
-        p.cancel = d.d_cancel;
-        p.framebuffer = ctx->d_fb;
-        p.band_done = use_bands ? band_counters(ctx) : nullptr;
-        p.band_rows = ctx->band_rows;
-        p.band_local = (ctx->shard_world * n_dev > 1 || ctx->fb_imported) ? d.d_strip_counter + 32 : nullptr; // own cache line
-        std::memset(p.band_share, 0, sizeof(p.band_share));
-        if (use_bands)
-            std::memcpy(p.band_share, ctx->band_share[p.shard_rank].data(), sizeof(p.band_share));
-        p.band_scope_sys = (ctx->fb_imported || i > 0 || ctx->shard_signals || std::getenv("RTM_BAND_SYS")) ? 1u : 0u;
-        p.hit_tri = keep_hits ? ctx->d_hit_tri : nullptr;
-        p.hit_t = keep_hits ? ctx->d_hit_t : nullptr;
-        p.hit_u = keep_hits ? ctx->d_hit_u : nullptr;
-        p.hit_v = keep_hits ? ctx->d_hit_v : nullptr;
-        p.counters = d.d_counters;
-        {
-            const float one[2] = { 1.0f, 1.0f }, minus_one[2] = { -1.0f, -1.0f };
-            std::memcpy(&p.pk_one, one, sizeof(p.pk_one));
-            std::memcpy(&p.pk_minus_one, minus_one, sizeof(p.pk_minus_one));
-        }
-
-        {
-            const uint64_t chunks_total = (total + p.shard_chunk - 1) / p.shard_chunk;
-            const uint64_t my_chunks = (chunks_total + p.shard_world - 1) / p.shard_world;
-            if (my_chunks * p.shard_chunk >= (1ull << 32))
-                return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: too many strips");
-            p.shard_strips = (uint32_t) (my_chunks * p.shard_chunk);
-
-            // cost order from the previous frame, valid only if that frame had the same layout
-            const uint32_t shard_strips = p.shard_strips;
-            std::vector<uint32_t> sig = { f->width, f->height, f->spp, n_tiles, (uint32_t) total, strip_w, strip_h,
-                                          p.shard_rank, p.shard_world, p.shard_chunk, shard_strips };
-            for (uint32_t k = 0; k < n_tiles; k++)
-            {
-                sig.push_back(rects[k].x ^ (rects[k].z << 16));
-                sig.push_back(rects[k].y ^ (rects[k].w << 16));
-            }
-            p.fetch_order = nullptr;
-            p.visit_cycles = nullptr;
-            // worth its ~1 % instrumentation cost when the frame is sharded or small (the tail of
-            // expensive strips is then a large part of the launch); RTM_COST_ORDER=0/1 forces it
-            const bool want_order = (ctx->cost_order_forced >= 0 ? ctx->cost_order_forced != 0
-                                    : (p.shard_world > 1 || (uint64_t) f->width * f->height * f->spp < (64ull << 20))) &&
-                                    shard_strips <= kVisitStripMask;
-            if (want_order && shard_strips > 0)
-            {
-                if (d.order_pending)
-                {
-                    CK(cudaStreamWaitEvent(d.stream, d.ev_order, 0)); // the order this frame follows / the buffers it reuses
-                    d.order_pending = false;
-                }
-                if (d.order_cap < shard_strips)
-                {
-                    CK(cudaStreamSynchronize(d.order_stream));
-                    cudaFree(d.d_strip_cycles); cudaFree(d.d_fetch_order); cudaFree(d.d_order_scratch); cudaFree(d.d_visit_cycles);
-                    d.d_strip_cycles = d.d_fetch_order = d.d_order_scratch = d.d_visit_cycles = nullptr;
-                    d.order_cap = 0;
-                    d.order_valid = false;
-                    CK(cudaMalloc(&d.d_strip_cycles, sizeof(uint32_t) * shard_strips));
-                    CK(cudaMalloc(&d.d_fetch_order, sizeof(uint32_t) * strip_order_capacity(shard_strips, 4)));
-                    CK(cudaMalloc(&d.d_visit_cycles, sizeof(uint32_t) * strip_order_capacity(shard_strips, 4)));
-                    CK(cudaMalloc(&d.d_order_scratch, sizeof(uint32_t) * strip_order_scratch_words(shard_strips)));
-                    if (!d.d_cost_sum)
-                        CK(cudaMalloc(&d.d_cost_sum, sizeof(unsigned long long)));
-                    if (!d.d_visit_total)
-                        CK(cudaMalloc(&d.d_visit_total, sizeof(uint32_t)));
-                    d.order_cap = shard_strips;
-                }
-                if (d.order_valid && sig == d.order_signature)
-                    p.fetch_order = d.d_fetch_order;
-                p.visit_total = d.d_visit_total;
-                d.order_signature = sig;
-                p.visit_cycles = d.d_visit_cycles;
-                CK(cudaMemsetAsync(d.d_visit_cycles, 0, sizeof(uint32_t) * strip_order_capacity(shard_strips, split_parts), d.stream));
-            }
-            else
-                d.order_valid = false;
-        }
-        // Moeller-Trumbore on origin-relative records when the per-camera pre-pass is negligible (a few M cell
-        // references: < 0.1 ms) -- not for the instrumented (counting) kernels; RTM_REL_RECORDS=0 switches it off;
-        // nor for small frames: measured +5..9 % on 33 M rays and more (4K and 1080p at 16 spp), -1 % on the 8 M rays
-        // of 1080p / 4 spp, -10 % on 512^2 / 1 spp, which is launch- and cold-miss-bound (the records are 64 B, not 48)
-        const bool rel_fits = ctx->desc.num_refs <= (4ull << 20) &&
-                              ((uint64_t) f->width * f->height * f->spp >= (16ull << 20) || ctx->rel_records_forced);
-        const bool alternates = ortho || p.shade_mode != 0;
-        // The packed-pair test pads odd lists with a triangle at x = -1e18 that no ray can hit as long as scene and
-        // camera stay within +-1e9 (pack.cu).  Anything larger takes the scalar test of the counting instantiation.
-        bool big_coords = false;
-        for (int k = 0; k < 3; k++)
-            big_coords = big_coords || !(std::fabs(ctx->desc.aabb_min[k]) < 1.0e9f) || !(std::fabs(ctx->desc.aabb_max[k]) < 1.0e9f) ||
-                         !(std::fabs(f->cam_mat[12 + k]) < 1.0e9f);
-        if (ortho)
-            big_coords = big_coords || !(std::fabs(p.cam.ortho_half_w) < 1.0e9f) || !(std::fabs(p.cam.ortho_half_h) < 1.0e9f);
-        if (alternates && big_coords)
-            return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: the orthographic camera / shading alternates need scene and "
-                                                 "camera coordinates within +-1e9");
-        const bool count_inst = ctx->counting || big_coords; // kernel instantiation with the scalar test (+ work counters)
-        if (alternates && ctx->counting)
-            return fail(ctx, CUDA_TRACE_ERR_ARG, "trace_tiles: the work counters are not available with the orthographic "
-                                                 "camera / shading alternates");
-        const uint32_t kvariant = alternates ? (uint32_t) kVariantMTAlt + f->variant
-                                  : (f->variant == kVariantMT && !count_inst && ctx->rel_records && rel_fits)
-                                      ? (uint32_t) kVariantMTRel : f->variant;
-        const size_t smem_bytes = trace_tiles_smem_bytes(f->spp, p.occ_smem_words);
-        const std::vector<long long> okey = { (long long) kvariant, keep_hits, count_inst, (long long) p.occ_mode, threads,
-                                              (long long) smem_bytes };
-        if (okey != d.occupancy_key)
-        {
-            d.blocks_per_sm = std::max(1, trace_tiles_max_blocks_per_sm(kvariant, keep_hits, count_inst, (int) p.occ_mode,
-                                                                        threads, smem_bytes));
-            d.occupancy_key = okey;
-        }
-        const int per_sm = d.blocks_per_sm;
-        const uint64_t my_strips = (total + p.shard_world - 1) / p.shard_world;
-        const uint64_t want = (my_strips + (threads / 32) - 1) / (threads / 32);
-        const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) d.sm_count * per_sm, want));
-        {
-            // How many finished strips a warp collects before it publishes them to the band counters: the fence
-            // costs ~1 us, but a held-back strip delays its band's read-back -- at most 1/16 of a warp's share
-            // of the frame (8 strips for a whole 4K frame on one GPU, every strip for an eighth of it)
-            const uint64_t warps = (uint64_t) blocks * (threads / 32);
-            uint64_t hold = std::min<uint64_t>(8, std::max<uint64_t>(1, my_strips / std::max<uint64_t>(1, warps * 16)));
-            if (const char *e = std::getenv("RTM_BAND_FLUSH")) // tuning override (experiments only): strips held, 1..8
-                hold = (uint64_t) std::min(8, std::max(1, std::atoi(e)));
-            p.band_flush_units = (uint32_t) hold * split_parts;
-        }
-        if (i == 0)
-            ctx->t_launching_ms = ms_since(ctx->t_enter);
-        CK(cudaEventRecord(d.ev_begin, d.stream));
-        if (kvariant == kVariantMTRel && total)
-        {
-            // records relative to this frame's camera position: rebuilt (inside the timed region) when it moved
-            if (!d.d_pair_recs_rel)
-                CK(cudaMalloc(&d.d_pair_recs_rel, std::max<uint64_t>(ctx->num_pairs, 1) * 7 * sizeof(float4)));
-            if (!d.rel_valid || std::memcmp(d.rel_origin, p.cam.origin, sizeof(d.rel_origin)) != 0)
-            {
-                launch_origin_relative_pairs(d.d_pair_recs, std::max<uint64_t>(ctx->num_pairs, 1), p.cam.origin, d.d_pair_recs_rel, d.stream);
-                ctx->launches++;
-                std::memcpy(d.rel_origin, p.cam.origin, sizeof(d.rel_origin));
-                d.rel_valid = true;
-            }
-            p.grid.pair_recs_rel = d.d_pair_recs_rel;
-        }
-        if (total)
-        {
-            launch_trace_tiles(p, kvariant, keep_hits, count_inst, blocks, threads, d.stream);
-            ctx->launches++;
-        }
-        if (i == 0)
-            ctx->t_launched_ms = ms_since(ctx->t_enter);
-        CK(cudaEventRecord(d.ev_end, d.stream));
-        CK(cudaMemcpyAsync(d.h_cancel_seen, d.d_cancel, sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
-        if (p.visit_cycles && total)
-        {
-            // this frame's strip costs -> next frame's visiting order (off the timed kernel)
-            CK(cudaEventRecord(d.ev_traced, d.stream));
-            CK(cudaStreamWaitEvent(d.order_stream, d.ev_traced, 0));
-            launch_build_strip_order(d.d_visit_cycles, p.fetch_order != nullptr, d.d_strip_cycles, (uint32_t) d.order_signature[10],
-                                     split_parts, d.d_cost_sum, d.d_order_scratch, d.d_visit_total, d.d_fetch_order, d.order_stream);
-            CK(cudaEventRecord(d.ev_order, d.order_stream));
-            d.order_pending = true;
-            ctx->launches += 5;
-            d.order_valid = true;
-        }
-        CK(cudaGetLastError());
-        d.frame_pending = true;
+        if ((rc = launch_on_device(ctx, i, f, kind, use_bands, seq)))
+            return rc;
+        if (i == 0 && can_overlap && (rc = enqueue_band_copies(ctx, f, host_bgra, expected)))
+            return rc;
     }
-
-    if (can_overlap)
-    {
-        DeviceState& d0 = ctx->dev[0];
-        CK(cudaSetDevice(d0.ordinal));
-        uint32_t *counters = band_counters(ctx);
-        for (uint32_t b = 0; b < ctx->n_bands; b++)
-        {
-            const uint32_t y0 = b * ctx->band_rows, y1 = std::min(f->height, y0 + ctx->band_rows);
-            if (ctx->wait_value32(d0.copy_stream, (unsigned long long) (uintptr_t) (counters + b), ctx->band_expected[b],
-                                  0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
-                return fail(ctx, CUDA_TRACE_ERR_CUDA, "cuStreamWaitValue32 failed");
-            CK(cudaMemcpyAsync(host_bgra + (size_t) y0 * f->width, ctx->d_fb + (size_t) y0 * f->width,
-                               (size_t) (y1 - y0) * f->width * sizeof(uint32_t), cudaMemcpyDeviceToHost, d0.copy_stream));
-        }
-        ctx->copy_pending = true;
-    }
+    std::memcpy(ctx->band_expected, expected, sizeof(expected));
+    ctx->band_dirty = false;
+    for (DeviceState& d : ctx->dev)
+        if ((rc = enqueue_order_followup(ctx, d)))
+            return rc;
     return 0;
 }
+
+extern "C"
+{
 
 int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *f, const cuda_trace_tile_rect *tiles,
                            uint32_t n_tiles)
@@ -1208,6 +1403,7 @@ int cuda_trace_sync(cuda_trace_ctx *ctx)
 {
     if (!ctx)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     bool any = false, cancelled = false;
     float ms_max = 0.0f;
     for (DeviceState& d : ctx->dev)
@@ -1221,7 +1417,7 @@ int cuda_trace_sync(cuda_trace_ctx *ctx)
             float ms = 0.0f;
             CK(cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
             ms_max = std::max(ms_max, ms);
-            cancelled = cancelled || *(volatile uint32_t *) d.h_cancel_seen != 0; // copied out behind the kernel
+            cancelled = cancelled || *(volatile uint32_t *) d.h_cancel_seen == d.launched_seq; // stored by the kernel itself
             d.frame_pending = false;
             any = true;
         }
@@ -1241,11 +1437,19 @@ int cuda_trace_sync(cuda_trace_ctx *ctx)
     return 0;
 }
 
+// Not serialised with the other entry points: it is meant to be called while cuda_trace_tiles / cuda_trace_sync
+// block in another thread.  The cancel word names the frame it is meant for (its sequence number), is never
+// cleared, and the kernel compares it with its own number: a request that lands late cannot stop a later frame, and
+// one that arrives while the frame is still being set up on the host is not lost.
 int cuda_trace_cancel(cuda_trace_ctx *ctx)
 {
     if (!ctx)
         return CUDA_TRACE_ERR_ARG;
-    std::lock_guard<std::mutex> guard(ctx->cancel_mtx);
+    const uint32_t seq = ctx->frame_seq.load();
+    if (seq == 0)
+        return 0; // nothing was ever launched
+    ctx->cancel_seq.store(seq);
+    *(volatile uint32_t *) ctx->pinned_cancel_src = seq;
     for (DeviceState& d : ctx->dev)
     {
         if (cudaSetDevice(d.ordinal) != cudaSuccess)
@@ -1261,6 +1465,7 @@ int cuda_trace_read_framebuffer(cuda_trace_ctx *ctx, uint32_t *host_bgra)
 {
     if (!ctx || !host_bgra)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     if (!ctx->d_fb || !ctx->frame_valid)
         return fail(ctx, CUDA_TRACE_ERR_ARG, "read_framebuffer: no frame rendered");
     DeviceState& d0 = ctx->dev[0];
@@ -1268,11 +1473,8 @@ int cuda_trace_read_framebuffer(cuda_trace_ctx *ctx, uint32_t *host_bgra)
     const uint32_t w = ctx->fb_w, h = ctx->fb_h;
     const size_t bytes = (size_t) w * h * sizeof(uint32_t);
 
-    // whole frame covered by a single tile list? then one copy, else one 2-D copy per tile
-    uint64_t covered = 0;
-    for (const auto& t : ctx->tiles)
-        covered += (uint64_t) (t.x1 - t.x0) * (t.y1 - t.y0);
-    if (covered >= (uint64_t) w * h)
+    // the tile list partitions the whole frame? then one copy, else one 2-D copy per tile
+    if (ctx->plan.covers_frame && ctx->plan.width == w && ctx->plan.height == h)
         CK(cudaMemcpyAsync(host_bgra, ctx->d_fb, bytes, cudaMemcpyDeviceToHost, d0.stream));
     else
         for (const auto& t : ctx->tiles)
@@ -1292,6 +1494,7 @@ int cuda_trace_tiles(cuda_trace_ctx *ctx, const cuda_trace_frame *frame, const c
 {
     if (!ctx)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     ctx->t_enter = std::chrono::steady_clock::now();
     int rc = tiles_async_impl(ctx, frame, tiles, n_tiles, host_bgra);
     if (rc)
@@ -1313,6 +1516,7 @@ int cuda_trace_last_call_timing(cuda_trace_ctx *ctx, double ms[7])
 {
     if (!ctx || !ms)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     ms[0] = ctx->t_submitted_ms; ms[1] = ctx->t_traced_ms; ms[2] = ctx->t_copied_ms; ms[3] = ctx->t_return_ms;
     ms[4] = ctx->t_prepared_ms; ms[5] = ctx->t_launching_ms; ms[6] = ctx->t_launched_ms;
     return 0;
@@ -1322,6 +1526,7 @@ int cuda_trace_last_kernel_ms(cuda_trace_ctx *ctx, float *ms)
 {
     if (!ctx || !ms)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     int rc = cuda_trace_sync(ctx);
     if (rc)
         return rc;
@@ -1333,6 +1538,7 @@ int cuda_trace_download_hits(cuda_trace_ctx *ctx, uint32_t *tri_idx, float *t, f
 {
     if (!ctx)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     int rc = cuda_trace_sync(ctx);
     if (rc)
         return rc;
@@ -1352,6 +1558,7 @@ static int intersect_rays_impl(cuda_trace_ctx *ctx, uint32_t n, const float *ori
 {
     if (!ctx || (n && (!origins || !dirs || !tri_idx || !t || !u || !v)) || variant > 1)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     if (!ctx->have_scene)
         return fail(ctx, CUDA_TRACE_ERR_NO_SCENE, "intersect_rays: upload a scene first");
     if (n == 0)
@@ -1399,6 +1606,7 @@ int cuda_trace_ray_march(cuda_trace_ctx *ctx, uint32_t n, const float *origins, 
 {
     if (!ctx || (n && (!origins || !dirs || !hit || !t)))
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     if (!ctx->have_scene)
         return fail(ctx, CUDA_TRACE_ERR_NO_SCENE, "ray_march: upload a scene first");
     if (n == 0)
@@ -1425,6 +1633,7 @@ int cuda_trace_sample_table(cuda_trace_ctx *ctx, uint32_t spp, float *xy)
 {
     if (!ctx || !xy || spp == 0)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     DeviceState& d = ctx->dev[0];
     CK(cudaSetDevice(d.ordinal));
     float2 *d_smp = nullptr;
@@ -1461,6 +1670,7 @@ int cuda_trace_qmc_sequence(cuda_trace_ctx *ctx, uint32_t kind, uint32_t scrambl
 {
     if (!ctx || (!out && count && dim_count) || kind > 6 || scramble > 4)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     const bool table_kind = kind <= 3;
     if (table_kind && ((uint64_t) dim_begin + dim_count > (uint64_t) kQmcPrimes))
         return fail(ctx, CUDA_TRACE_ERR_ARG, "qmc_sequence: dimension beyond the 1000-prime table");
@@ -1531,6 +1741,7 @@ int cuda_trace_qmc_cranley_patterson(cuda_trace_ctx *ctx, const double *x, doubl
 {
     if (!ctx || (count && (!x || !out)))
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     if (count == 0)
         return 0;
     DeviceState& d = ctx->dev[0];
@@ -1552,6 +1763,7 @@ int cuda_trace_get_counters(cuda_trace_ctx *ctx, cuda_trace_counters *out)
 {
     if (!ctx || !out)
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     int rc = cuda_trace_sync(ctx);
     if (rc)
         return rc;
@@ -1601,13 +1813,14 @@ int cuda_trace_download_strip_cycles(cuda_trace_ctx *ctx, uint32_t *cycles, uint
 {
     if (!ctx || !count || (capacity && !cycles))
         return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     int rc = cuda_trace_sync(ctx);
     if (rc)
         return rc;
     DeviceState& d = ctx->dev[0];
     CK(cudaSetDevice(d.ordinal));
     CK(cudaStreamSynchronize(d.order_stream));
-    *count = (d.order_valid && d.order_signature.size() > 10) ? d.order_signature[10] : 0;
+    *count = d.order_valid ? d.order_strips : 0;
     const uint64_t n = std::min<uint64_t>(*count, capacity);
     if (n)
     {

@@ -68,7 +68,11 @@ __device__ __forceinline__ void release_add(const TraceParams& p, uint32_t band,
 {
     if (!p.band_local) // a single GPU rendering into its own framebuffer: one level, the band counter counts pieces
     {
-        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(count) : "memory");
+        // (system scope when a copy engine waits on the counter and reads the pixels: it is not in this GPU's .gpu scope)
+        if (p.band_scope_sys)
+            asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(count) : "memory");
+        else
+            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(count) : "memory");
         return;
     }
     uint32_t before;
@@ -140,8 +144,10 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
         bool cancel_seen = false;
         if (lane == 0)
         {
-            cancel_seen = *(volatile const uint32_t *) p.cancel != 0;
+            cancel_seen = *(volatile const uint32_t *) p.cancel == p.frame_seq;
             visit = atomicAdd(p.strip_counter, 1u);
+            if (cancel_seen) // tell the host (mapped memory; only ever on a cancelled frame)
+                *(volatile uint32_t *) p.cancel_seen = p.frame_seq;
         }
         visit = __shfl_sync(kFull, visit, 0);
         // a VOTE result is warp-uniform by construction, which lets the compiler keep the traversal

@@ -68,7 +68,9 @@ struct TraceParams
     uint32_t split_parts;              // pieces an expensive strip is visited in (strip_split_parts); band counters count pieces
     uint32_t *visit_cycles;            // out: cycles spent per visit (feeds the next frame's order, schedule.cu) or null
     uint32_t *strip_counter;           // dynamic strip scheduler (zeroed before launch)
-    const uint32_t *cancel;            // non-zero => stop fetching strips
+    const uint32_t *cancel;            // == frame_seq => stop tracing (the word names the frame to cancel, api.cu)
+    uint32_t frame_seq;
+    uint32_t *cancel_seen;             // host-mapped word: a warp that saw the request stores frame_seq there
     uint32_t *framebuffer;             // width * height, row 0 = y 0 (may be a peer / IPC pointer)
     uint32_t *band_done;               // per row band: GPUs whose share of the band is finished (monotone across frames;
                                        // lives behind the framebuffer, so peers / other ranks reach it through the

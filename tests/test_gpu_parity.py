@@ -177,14 +177,16 @@ def test_arbitrary_rays(cuda_trace, port, scene_data):
 
 @pytest.mark.parametrize("mode", ["0", "1", "2"])
 @pytest.mark.parametrize("name,spp", [("killeroo", 4), ("room", 16), ("cornell", 1)])
-def test_occupancy_map_modes(cuda_trace, port, scene_data, monkeypatch, mode, name, spp):
+def test_occupancy_map_modes(port, scene_data, monkeypatch, mode, name, spp):
     """The three homes of the padded occupancy map (bits through L1 / bits in shared memory / one byte
     per cell in shared memory with the DDA tracking the byte address) and both phase-A forms must give
-    the same bits.  Small frames default to mode 0, so the shared-memory modes are forced here."""
+    the same bits.  Small frames default to mode 0, so the shared-memory modes are forced here (the tuning
+    switches are read when a context is created)."""
     monkeypatch.setenv("RTM_OCC_MODE", mode)
     monkeypatch.setenv("RTM_THREADS", "1024" if mode != "0" else "256")
     sd = scene_data(name)
     w, h = 256, 144
+    cuda_trace = pkg("capi").CudaTrace(1)
     cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
     f = frame_for(cuda_trace, port, sd, w, h, spp, keep_hits=True)
     img = cuda_trace.trace_tiles(f)
@@ -195,6 +197,7 @@ def test_occupancy_map_modes(cuda_trace, port, scene_data, monkeypatch, mode, na
     # and the plain (non-instrumented) kernel instantiation
     f2 = frame_for(cuda_trace, port, sd, w, h, spp)
     assert np.array_equal(cuda_trace.trace_tiles(f2), o["bgra"])
+    cuda_trace.close()
 
 
 @pytest.mark.parametrize("mode", ["0", "2"])
@@ -394,4 +397,67 @@ def test_cost_ordered_split_frames_match_image_order(ref, scene_data):
         assert np.array_equal(pinned.array, want[k]), "frame %d (overlapped read-back)" % k
     heavy = ct.strip_cycles()
     assert heavy.max() > 4 * heavy.mean()  # the premise: strip costs are very uneven
+    ct.close()
+
+
+def test_refused_call_leaves_the_overlapped_read_back_usable(port, scene_data):
+    """A call that is refused (bad sample count, tile outside the frame, counters with an alternate) must not
+    advance the band completion targets of the overlapped read-back: the next ordinary frame into a host buffer
+    would then wait for counts the device never reaches.  Also after a frame whose layout differs."""
+    capi = pkg("capi")
+    sd = scene_data("cornell")
+    w, h, spp = 640, 480, 4   # > 1 MB of pixels: several row bands
+    ct = capi.CudaTrace(1)
+    ct.upload_scene(sd.vtx, sd.tri, 64)
+    fov_xs, aspect = port.camera_constants(sd.fov, w, h)
+    good = ct.make_frame(w, h, spp, sd.cam16, fov_xs, aspect)
+    ref_img = ct.trace_tiles(good).copy()
+    assert np.array_equal(ref_img, port.scene(sd.vtx, sd.tri, 64).render(sd.cam16, sd.fov, w, h, spp)["bgra"])
+    # 1. sample count beyond the limit
+    with pytest.raises(capi.CudaTraceError):
+        ct.trace_tiles(ct.make_frame(w, h, 1 << 20, sd.cam16, fov_xs, aspect))
+    assert np.array_equal(ct.trace_tiles(good), ref_img)
+    # 2. a tile outside the frame
+    with pytest.raises(capi.CudaTraceError):
+        ct.trace_tiles(good, rects=[(0, 0, w + 1, h)])
+    assert np.array_equal(ct.trace_tiles(good), ref_img)
+    # 3. work counters together with the orthographic camera
+    ct.set_counting(True)
+    with pytest.raises(capi.CudaTraceError):
+        ct.trace_tiles(ct.make_frame(w, h, spp, sd.cam16, fov_xs, aspect, ortho_width=1.5))
+    ct.set_counting(False)
+    assert np.array_equal(ct.trace_tiles(good), ref_img)
+    # 4. overlapping tiles whose areas add up to the frame: not a partition, so no whole-band copies; pixels no
+    #    tile covers keep what the host buffer held
+    out = np.full((h, w), 0xDEADBEEF, np.uint32)
+    ct.trace_tiles(good, rects=[(0, 0, w, h // 2), (0, 0, w, h // 2)], out=out)
+    assert np.array_equal(out[: h // 2], ref_img[: h // 2]) and (out[h // 2:] == 0xDEADBEEF).all()
+    assert np.array_equal(ct.trace_tiles(good), ref_img)
+    ct.close()
+
+
+def test_cancel_names_its_frame(port, scene_data):
+    """cuda_trace_cancel stops the frame in flight (Framebuffer::m_threads_stop, framebuffer.h:32) and nothing
+    else: a request issued when no frame is running must not cancel the next one."""
+    import threading
+    capi = pkg("capi")
+    sd = scene_data("killeroo")
+    w, h, spp = 1920, 1080, 64   # long enough (tens of ms) for the request to arrive while it runs
+    ct = capi.CudaTrace(1)
+    ct.upload_scene(sd.vtx, sd.tri, 64)
+    fov_xs, aspect = port.camera_constants(sd.fov, w, h)
+    f = ct.make_frame(w, h, spp, sd.cam16, fov_xs, aspect)
+    small = ct.make_frame(160, 96, 4, sd.cam16, *port.camera_constants(sd.fov, 160, 96))
+    want_small = port.scene(sd.vtx, sd.tri, 64).render(sd.cam16, sd.fov, 160, 96, 4)["bgra"]
+    ct.trace_tiles(small)
+    ct.cancel()  # no frame running: refers to the finished frame
+    assert np.array_equal(ct.trace_tiles(small), want_small)
+    ct.trace_tiles_async(f)
+    t = threading.Timer(0.002, ct.cancel)
+    t.start()
+    with pytest.raises(capi.CudaTraceError) as e:
+        ct.sync()
+    t.join()
+    assert e.value.code == 5  # CUDA_TRACE_ERR_CANCELLED
+    assert np.array_equal(ct.trace_tiles(small), want_small)   # the next frame is not affected
     ct.close()
