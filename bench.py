@@ -445,6 +445,33 @@ def bench_side_config(name, steps, rank, world, local_rank, group):
     return rec
 
 
+def time_class_route(wl, steps, n_gpus=1):
+    """The drop-in route a viewer written against the reference takes (application.cpp:304-517): Mesh -> Scene ->
+    Renderer, then per frame StartRendering() ... WaitRendering() with the pixels in the Framebuffer::Tile buffers
+    (host/*.h, INTEGRATION.md route A).  Timed inside the C++ classes, from the StartRendering call to the last
+    tile handed back; L2 flushed before every frame."""
+    capi, hostapi, scenes = pkg("capi"), pkg("hostapi"), pkg("scenes")
+    w, h, spp = wl["width"], wl["height"], wl["spp"]
+    mesh, fov, cam = scenes.build(hostapi.host_api(), wl["scene"])
+    hr = hostapi.HostRenderer(mesh, fov, cam, wl["grid_res"], n_gpus)
+    for _ in range(3):
+        hr.start(w, h, spp)
+        hr.wait()
+    total = 0.0
+    for _ in range(steps):
+        for dev in range(n_gpus):
+            capi.flush_l2(dev)
+        hr.start(w, h, spp)
+        total += hr.wait()
+    img = hr.copy_bitmap(w, h)
+    kernel_ms = hr.last_kernel_ms()
+    hr.close()
+    key, gold = golden_digest(wl)
+    return {"value": w * h * spp * steps / total / 1e6, "unit": METRIC, "ms_per_step": 1e3 * total / steps, "n_gpus": n_gpus,
+            "kernel_ms_last": kernel_ms, "what": "Renderer::StartRendering() -> WaitRendering(), pixels in the Framebuffer::Tile buffers",
+            "image_md5_ok": (md5(img) == gold["image_md5"]) if gold else None}
+
+
 def run_ours(args, wl, rank, world, local_rank, dist):
     multirank = pkg("multirank")
     group = multirank.RankGroup(dist, "cuda" if dist is not None else None)
@@ -469,6 +496,7 @@ def run_ours(args, wl, rank, world, local_rank, dist):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base = time_reference_cpu(wl, 3, 1, budget_s=30.0)
     par = g.parity(cpu_rows=base["rows"] if base else None)
+    class_route = time_class_route(wl, args.steps) if (rank == 0 and world == 1 and not args.no_class_route) else None
     side = {}
     if not args.no_side_configs:
         names = [n for n in ("C1", "C2", "C3", "C4") if n != wl["name"]]
@@ -505,12 +533,16 @@ def run_ours(args, wl, rank, world, local_rank, dist):
                   "strips": "~128-ray pixel-block strips, chunks of 32 strips dealt round-robin over ranks",
                   "scene_upload_and_grid_build_s": upload_s, "configs": side},
     }
+    if class_route:
+        line["e2e"]["class_route"] = class_route
     if base:
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_baseline"].update(ms_per_frame_est=base["ms_per_frame_est"], ms_per_frame_best=base["ms_per_frame_best"])
     print(json.dumps(line), flush=True)
     bad = [n for n, p in [(wl["name"], par)] + [(n, r["parity"]) for n, r in side.items()]
            if p.get("image_md5_ok") is False or p.get("hits_ok") is False or p.get("rows_ok") is False]
+    if class_route and class_route["image_md5_ok"] is False:
+        bad.append(wl["name"] + " (class route)")
     if bad:
         sys.stderr.write("PARITY FAILURE: %s differ from the reference digests\n" % ", ".join(bad))
         return 3
@@ -526,6 +558,7 @@ def main():
     ap.add_argument("--workload", default="killeroo4k")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-configs", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--no-class-route", action="store_true", help="skip the Renderer / Framebuffer class-route timing")
     ap.add_argument("--full", action="store_true", help="also run C5 (50 M triangles) among the side configs")
     args = ap.parse_args()
     args.steps = max(args.steps, 1)

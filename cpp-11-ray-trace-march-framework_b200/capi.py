@@ -59,6 +59,8 @@ SYMBOLS = {
                                                     C.POINTER(GridDesc), _U64P, _U32P]),
     "cuda_trace_download_grid": (C.c_int, [C.c_void_p, C.POINTER(GridDesc), _U64P, _U32P]),
     "cuda_trace_tiles": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.POINTER(TileRect), C.c_uint32, _U32P]),
+    "cuda_trace_tiles_into": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.POINTER(TileRect), C.c_uint32, C.POINTER(_U32P),
+                                        C.c_void_p, C.c_void_p]),
     "cuda_trace_tiles_async": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.POINTER(TileRect), C.c_uint32]),
     "cuda_trace_sync": (C.c_int, [C.c_void_p]),
     "cuda_trace_read_framebuffer": (C.c_int, [C.c_void_p, _U32P]),
@@ -320,6 +322,24 @@ class CudaTrace:
         self._ck(self.lib.cuda_trace_tiles(self.h, C.byref(frame), tiles, n_tiles,
                                            _p(out, _U32P) if want_image else None))
         return out
+
+    def trace_tiles_into(self, frame, rects=None):
+        """cuda_trace_tiles_into: every tile into its own page-locked buffer.  -> (list of [th, tw] uint32 arrays,
+        list of tile-index groups in the order the library reported them complete)"""
+        if rects is None:
+            rects = full_frame_tiles(frame.width, frame.height)
+        tiles, n_tiles = self.make_tiles(rects)
+        pinned = [PinnedImage(max(tiles[i].x1 - tiles[i].x0, 1), max(tiles[i].y1 - tiles[i].y0, 1)) for i in range(n_tiles)]
+        ptrs = (_U32P * max(n_tiles, 1))(*[C.cast(p.ptr, _U32P) for p in pinned])
+        groups = []
+        cb_type = C.CFUNCTYPE(None, _U32P, C.c_uint32, C.c_void_p)
+        cb = cb_type(lambda idx, n, user: groups.append([int(idx[k]) for k in range(n)]))
+        rc = self.lib.cuda_trace_tiles_into(self.h, C.byref(frame), tiles, n_tiles, ptrs, C.cast(cb, C.c_void_p), None)
+        out = [p.array.copy() for p in pinned]
+        for p in pinned:
+            p.close()
+        self._ck(rc)
+        return out, groups
 
     def trace_tiles_async(self, frame, rects=None):
         if rects is None:

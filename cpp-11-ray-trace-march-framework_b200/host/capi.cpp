@@ -161,7 +161,11 @@ double rtm_renderer_render(void *h, uint32 width, uint32 height, uint32 spp, uin
             r->Resize(width, height);
         else
             r->StartRendering();
-        r->WaitRendering();
+        if (!r->WaitRendering())
+        {
+            g_error = r->GetLastError();
+            return -1.0;
+        }
         const auto t1 = std::chrono::steady_clock::now();
         if (bgra)
             r->CopyToBitmap(bgra);
@@ -173,6 +177,38 @@ double rtm_renderer_render(void *h, uint32 width, uint32 height, uint32 spp, uin
         return -1.0;
     }
 }
+// The asynchronous form a viewer uses: start (returns at once), poll / save screenshots, wait
+int rtm_renderer_start(void *h, uint32 width, uint32 height, uint32 spp)
+{
+    Renderer *r = static_cast<HostRenderer *>(h)->renderer.get();
+    try
+    {
+        r->WaitRendering();
+        r->SetSampleCount(spp);
+        if (r->GetWidth() != width || r->GetHeight() != height)
+            r->Resize(width, height);
+        else
+            r->StartRendering();
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_error = e.what();
+        return -1;
+    }
+}
+int rtm_renderer_wait(void *h)
+{
+    Renderer *r = static_cast<HostRenderer *>(h)->renderer.get();
+    if (r->WaitRendering())
+        return 0;
+    g_error = r->GetLastError();
+    return -1;
+}
+void rtm_renderer_stop(void *h) { static_cast<HostRenderer *>(h)->renderer->StopRendering(); }
+uint32 rtm_renderer_finished_tiles(void *h) { return static_cast<HostRenderer *>(h)->renderer->CountFinishedTiles(); }
+double rtm_renderer_last_render_seconds(void *h) { return static_cast<HostRenderer *>(h)->renderer->GetLastRenderSeconds(); }
+void rtm_renderer_copy_bitmap(void *h, uint32 *bgra) { static_cast<HostRenderer *>(h)->renderer->CopyToBitmap(bgra); }
 void rtm_renderer_set_alternates(void *h, float ortho_width, uint32 shade_mode)
 {
     Renderer *r = static_cast<HostRenderer *>(h)->renderer.get();

@@ -15,7 +15,6 @@ Renderer::~Renderer()
 {
     KillAllWorkerThreads();
     WaitRendering();
-    cuda_trace_host_free(m_frame);
 }
 
 void Renderer::SetSampleCount(uint cnt)
@@ -62,36 +61,32 @@ void Renderer::RenderTiles(Tile * const *tiles, uint count)
     std::memcpy(frame.cam_mat, cam_mat.m_mat, sizeof(frame.cam_mat));
 
     std::vector<cuda_trace_tile_rect> rects(count);
+    std::vector<uint32 *> buffers(count);
     for (uint i = 0; i < count; i++)
-        tiles[i]->GetPosition(rects[i].x0, rects[i].y0, rects[i].x1, rects[i].y1);
-
-    if (m_frame_pixels != size_t(m_width) * m_height)
     {
-        cuda_trace_host_free(m_frame);
-        m_frame_pixels = size_t(m_width) * m_height;
-        m_frame = static_cast<uint32 *>(cuda_trace_host_alloc(m_frame_pixels * sizeof(uint32)));
-        if (!m_frame)
-        {
-            m_frame_pixels = 0;
-            throw std::runtime_error("Renderer: cannot allocate the host frame staging buffer");
-        }
+        tiles[i]->GetPosition(rects[i].x0, rects[i].y0, rects[i].x1, rects[i].y1);
+        buffers[i] = tiles[i]->GetBuffer(); // index x + y * tile_width, as the reference's kernel writes it (renderer.cpp:133)
     }
-    const int rc = cuda_trace_tiles(ctx, &frame, rects.data(), count, m_frame);
+
+    // One launch for the whole list; every tile is copied from the device framebuffer straight into its own
+    // (page-locked) buffer as soon as the rows it lies in are traced, and handed back -- unlocked -- right then
+    struct Done
+    {
+        Renderer *self;
+        Tile * const *tiles;
+        static void Call(const uint32_t *idx, uint32_t n, void *user)
+        {
+            Done *d = static_cast<Done *>(user);
+            for (uint32_t k = 0; k < n; k++)
+                d->self->TileFinished(*d->tiles[idx[k]]);
+        }
+    } done = { this, tiles };
+    const int rc = cuda_trace_tiles_into(ctx, &frame, rects.data(), count, buffers.data(), &Done::Call, &done);
     if (rc == CUDA_TRACE_ERR_CANCELLED)
         return;
     if (rc)
-        throw std::runtime_error(std::string("Renderer: cuda_trace_tiles failed: ") + cuda_trace_last_error(ctx));
+        throw std::runtime_error(std::string("Renderer: cuda_trace_tiles_into failed: ") + cuda_trace_last_error(ctx));
     cuda_trace_last_kernel_ms(ctx, &m_last_kernel_ms);
-
-    // scatter into the tiles' own buffers (index x + y * tile_width, reference renderer.cpp:133)
-    for (uint i = 0; i < count; i++)
-    {
-        Tile& t = *tiles[i];
-        uint32 *dst = t.GetBuffer();
-        const uint tw = t.GetWidth();
-        for (uint y = 0; y < t.GetHeight(); y++)
-            std::memcpy(dst + size_t(y) * tw, &m_frame[rects[i].x0 + size_t(rects[i].y0 + y) * m_width], size_t(tw) * 4);
-    }
 }
 
 bool Renderer::RayMarch(Vec3f origin, Vec3f dir, float& t)

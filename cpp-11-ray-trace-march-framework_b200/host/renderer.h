@@ -1,7 +1,8 @@
 // Renderer = Framebuffer + Scene, the reference's top-level rendering object (renderer.h:11-35):
 // Renderer(unique_ptr<Scene>), SetSampleCount / GetSampleCount, RenderTile override.  The per-tile
 // kernel itself (reference renderer.cpp:43-136) runs on the GPU: RenderTile() is a one-tile
-// cuda_trace_tiles launch, RenderTiles() a single launch for the whole frame.
+// cuda_trace_tiles_into launch, RenderTiles() a single launch for the whole frame that hands tiles
+// back as they complete.
 #ifndef RTM_HOST_RENDERER_H
 #define RTM_HOST_RENDERER_H
 
@@ -49,8 +50,6 @@ protected:
     float m_ortho_width = 0.0f;
     uint m_shade_mode = 0;
     float m_last_kernel_ms = 0.0f;
-    uint32 *m_frame = nullptr;   // page-locked full-frame staging the device framebuffer is copied into
-    size_t m_frame_pixels = 0;
 };
 
 #endif

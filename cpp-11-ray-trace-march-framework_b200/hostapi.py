@@ -38,6 +38,14 @@ def load_host_library():
         lib.rtm_renderer_last_kernel_ms.restype = C.c_float
         lib.rtm_renderer_last_kernel_ms.argtypes = [C.c_void_p]
         lib.rtm_renderer_save_bmp.argtypes = [C.c_void_p, C.c_char_p]
+        lib.rtm_renderer_start.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        lib.rtm_renderer_wait.argtypes = [C.c_void_p]
+        lib.rtm_renderer_stop.argtypes = [C.c_void_p]
+        lib.rtm_renderer_finished_tiles.argtypes = [C.c_void_p]
+        lib.rtm_renderer_finished_tiles.restype = C.c_uint32
+        lib.rtm_renderer_last_render_seconds.argtypes = [C.c_void_p]
+        lib.rtm_renderer_last_render_seconds.restype = C.c_double
+        lib.rtm_renderer_copy_bitmap.argtypes = [C.c_void_p, _U32P]
         lib.rtm_renderer_device_context.restype = C.c_void_p
         lib.rtm_renderer_device_context.argtypes = [C.c_void_p]
         lib.rtm_renderer_intersect.restype = C.c_int
@@ -85,6 +93,28 @@ class HostRenderer:
         if sec < 0:
             raise RuntimeError("render failed: " + self.lib.rtm_last_error().decode())
         return sec, out
+
+    # -- the asynchronous form (Resize / StartRendering return at once, framebuffer.cpp:94-134)
+    def start(self, width, height, spp):
+        if self.lib.rtm_renderer_start(self.h, width, height, spp):
+            raise RuntimeError("start failed: " + self.lib.rtm_last_error().decode())
+
+    def wait(self):
+        """WaitRendering(); raises if the frame failed.  -> seconds from the start call to the last tile"""
+        if self.lib.rtm_renderer_wait(self.h):
+            raise RuntimeError("render failed: " + self.lib.rtm_last_error().decode())
+        return float(self.lib.rtm_renderer_last_render_seconds(self.h))
+
+    def stop(self):
+        self.lib.rtm_renderer_stop(self.h)
+
+    def finished_tiles(self):
+        return int(self.lib.rtm_renderer_finished_tiles(self.h))
+
+    def copy_bitmap(self, width, height):
+        out = np.zeros((height, width), np.uint32)
+        self.lib.rtm_renderer_copy_bitmap(self.h, out.ctypes.data_as(_U32P))
+        return out
 
     def set_alternates(self, ortho_width=0.0, shade_mode=0):
         """Renderer::SetOrthographicWidth / SetShadingMode (0 width = perspective; mode 0 = the live shading)."""

@@ -158,6 +158,17 @@ int cuda_trace_tiles_async(cuda_trace_ctx *ctx, const cuda_trace_frame *frame,
 int cuda_trace_sync(cuda_trace_ctx *ctx);
 int cuda_trace_read_framebuffer(cuda_trace_ctx *ctx, uint32_t *host_bgra);
 
+/* The same frame, but every tile lands in its OWN host buffer -- row-major within the tile, index x + y * tile_width:
+ * Framebuffer::Tile::m_bgra (framebuffer.h:64, written at renderer.cpp:133) -- and the caller learns of tiles as
+ * they complete: done(indices, count, user) is called ON THE CALLING THREAD, top of the frame first, once the pixels
+ * of tiles[indices[0 .. count)] are in host memory, while the rest of the frame is still being traced.  That is the
+ * moment the reference's worker releases the tile mutex (framebuffer.cpp:72-77), so a drop-in Framebuffer can let
+ * SaveToBMP / Draw see a frame in progress (framebuffer.cpp:163,203).  tile_bgra[i] should be page-locked
+ * (cuda_trace_host_alloc); `done` may be NULL.  Returns when the whole frame is on the host. */
+typedef void (*cuda_trace_tiles_done_fn)(const uint32_t *tile_indices, uint32_t count, void *user);
+int cuda_trace_tiles_into(cuda_trace_ctx *ctx, const cuda_trace_frame *frame, const cuda_trace_tile_rect *tiles,
+                          uint32_t n_tiles, uint32_t *const *tile_bgra, cuda_trace_tiles_done_fn done, void *user);
+
 /* Framebuffer::m_threads_stop (framebuffer.h:32): ask the running frame to stop early.  Safe to
  * call from another thread while cuda_trace_tiles / cuda_trace_sync block. */
 int cuda_trace_cancel(cuda_trace_ctx *ctx);

@@ -113,3 +113,98 @@ def test_grid_info_matches_reference(ref):
         assert np.float32(gi["cell_wdh"]).view(np.uint32) == np.float32(g["cell_wdh"]).view(np.uint32)
         for k in ("aabb_min", "aabb_max"):
             assert np.array_equal(gi[k].view(np.uint32), np.asarray(g[k], np.float32).view(np.uint32))
+
+
+def test_tiles_into_gives_every_tile_its_own_buffer(scene_data, port):
+    """cuda_trace_tiles_into: each tile row-major in its own buffer (Framebuffer::Tile::m_bgra, framebuffer.h:64),
+    reported complete in groups, every tile exactly once, top of the frame first."""
+    capi = pkg("capi")
+    sd = scene_data("killeroo")
+    w, h, spp = 1283, 731, 4   # ragged: the last tile column / row absorb the remainder
+    ct = capi.CudaTrace(1)
+    ct.upload_scene(sd.vtx, sd.tri, 64)
+    fov_xs, aspect = port.camera_constants(sd.fov, w, h)
+    f = ct.make_frame(w, h, spp, sd.cam16, fov_xs, aspect)
+    want = ct.trace_tiles(f)
+    rects = capi.full_frame_tiles(w, h)
+    for _ in range(2):
+        tiles, groups = ct.trace_tiles_into(f, rects)
+        for (x0, y0, x1, y1), t in zip(rects, tiles):
+            assert np.array_equal(t, want[y0:y1, x0:x1])
+        flat = [i for g in groups for i in g]
+        assert sorted(flat) == list(range(len(rects))) and len(groups) > 1
+        last_row = [rects[g[0]][3] for g in groups]
+        assert last_row == sorted(last_row)
+    # a partial, unordered tile list
+    some = [rects[40], rects[3], (5, 7, 5, 20), rects[100]]
+    tiles, groups = ct.trace_tiles_into(f, some)
+    for (x0, y0, x1, y1), t in zip(some, tiles):
+        if x1 > x0 and y1 > y0:
+            assert np.array_equal(t, want[y0:y1, x0:x1])
+    assert sorted(i for g in groups for i in g) == [0, 1, 2, 3]
+    ct.close()
+
+
+def test_screenshot_of_a_frame_in_progress(tmp_path):
+    """Tiles are handed back one by one while the frame is traced (the reference's worker leaves its tile lock
+    when the tile is done, framebuffer.cpp:72-77): a SaveToBMP during the frame shows the finished tiles with their
+    final pixels and the others black (framebuffer.cpp:203), and the count of lockable tiles grows."""
+    hr, _, _ = _host_renderer("killeroo")
+    w, h, spp = 1920, 1080, 256          # ~45 ms of tracing on one B200
+    hr.render(w, h, 1)                    # sizes the frame buffer
+    path = str(tmp_path / "partial.bmp")
+    hr.start(w, h, spp)
+    seen, shot, began = [], None, False
+    import time
+    t_end = time.time() + 10.0
+    while time.time() < t_end:
+        n = hr.finished_tiles()
+        seen.append(n)
+        began = began or n < 108          # the launcher holds the tiles: the frame has begun
+        if shot is None and 20 <= n < 100:
+            hr.save_bmp(path)
+            shot = n
+        if began and n == 108:
+            break
+    sec = hr.wait()
+    final = hr.copy_bitmap(w, h)
+    assert sec > 0 and shot is not None, "the frame went by without an intermediate state: %r" % sorted(set(seen))
+    assert any(0 < n < 108 for n in seen)
+    data = np.fromfile(path, np.uint8)[54:].view(np.uint32).reshape(h, w)
+    black = same = 0
+    for (x0, y0, x1, y1) in pkg("capi").full_frame_tiles(w, h):
+        t = data[y0:y1, x0:x1]
+        if not t.any():
+            black += 1
+        else:
+            assert np.array_equal(t, final[y0:y1, x0:x1])
+            same += 1
+    assert black > 0 and same >= shot
+
+
+def test_failed_frame_is_reported_not_fatal():
+    """A device error inside the launcher thread must not terminate the application (std::terminate from an
+    exception on a std::thread): WaitRendering() reports it, the tiles are released, the next frame works."""
+    hr, _, _ = _host_renderer("cornell")
+    _, good = hr.render(64, 48, 2)
+    with pytest.raises(RuntimeError) as e:
+        hr.render(64, 48, 1 << 20)   # more samples than the kernel accepts
+    assert "samples per pixel" in str(e.value)
+    assert hr.finished_tiles() == 108
+    _, again = hr.render(64, 48, 2)
+    assert np.array_equal(again, good)
+
+
+def test_stop_rendering_leaves_unfinished_tiles_black():
+    hr, _, _ = _host_renderer("killeroo")
+    w, h = 1920, 1080
+    hr.render(w, h, 1)
+    hr.start(w, h, 1024)                  # ~180 ms
+    while hr.finished_tiles() == 108:
+        pass
+    hr.stop()                             # KillAllWorkerThreads: cancel + wait
+    img = hr.copy_bitmap(w, h)
+    tiles = [img[y0:y1, x0:x1] for (x0, y0, x1, y1) in pkg("capi").full_frame_tiles(w, h)]
+    assert sum(1 for t in tiles if not t.any()) > 0
+    _, ok = hr.render(w, h, 1)            # and the renderer is still usable
+    assert ok.any()

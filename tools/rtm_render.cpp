@@ -96,7 +96,8 @@ int main(int argc, char **argv)
                 renderer.Resize(width, height);
             else
                 renderer.StartRendering();
-            renderer.WaitRendering();
+            if (!renderer.WaitRendering())
+                throw std::runtime_error(renderer.GetLastError());
             const double rays = double(width) * height * spp;
             std::printf("frame %u: %.3f ms wall, %.3f ms kernel, %.1f Mrays/s\n", f, renderer.GetLastRenderSeconds() * 1e3,
                         renderer.GetLastKernelMilliseconds(), rays / (renderer.GetLastKernelMilliseconds() * 1e3));
