@@ -58,6 +58,7 @@ SYMBOLS = {
     "cuda_trace_upload_scene_with_grid": (C.c_int, [C.c_void_p, _F32P, C.c_uint32, _U32P, C.c_uint32,
                                                     C.POINTER(GridDesc), _U64P, _U32P]),
     "cuda_trace_download_grid": (C.c_int, [C.c_void_p, C.POINTER(GridDesc), _U64P, _U32P]),
+    "cuda_trace_download_distance_map": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "cuda_trace_tiles": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.POINTER(TileRect), C.c_uint32, _U32P]),
     "cuda_trace_tiles_into": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.POINTER(TileRect), C.c_uint32, C.POINTER(_U32P),
                                         C.c_void_p, C.c_void_p]),
@@ -283,6 +284,18 @@ class CudaTrace:
         return dict(dim=np.array(list(d.dim), np.uint32), aabb_min=np.array(list(d.aabb_min), np.float32),
                     aabb_max=np.array(list(d.aabb_max), np.float32), cell_wdh=np.float32(d.cell_wdh),
                     inv_cell_wdh=np.float32(d.inv_cell_wdh), cell_offset=off, tri_index=idx[:int(d.num_refs)])
+
+    def download_distance_map(self):
+        """-> uint8 array [dim_y + 2, dim_z + 2, dim_x + 2] of the padded grid, or None when the scene has none"""
+        n = C.c_uint64(0)
+        self._ck(self.lib.cuda_trace_download_distance_map(self.h, None, C.byref(n)))
+        if n.value == 0:
+            return None
+        out = np.zeros(n.value, np.uint8)
+        self._ck(self.lib.cuda_trace_download_distance_map(self.h, out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        d = GridDesc()
+        self._ck(self.lib.cuda_trace_download_grid(self.h, C.byref(d), None, None))
+        return out.reshape(d.dim[1] + 2, d.dim[2] + 2, d.dim[0] + 2)
 
     # -- frames
     @staticmethod

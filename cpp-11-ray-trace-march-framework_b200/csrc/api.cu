@@ -49,6 +49,12 @@ struct DeviceState
     uint32_t *d_tri = nullptr;
     uint32_t *d_cell_start = nullptr, *d_cell_occ = nullptr, *d_tri_index = nullptr;
     uint32_t *d_pcell_start = nullptr, *d_pcell_occ = nullptr; // padded grid (rt_device.cuh)
+    uint8_t *d_pcell_dist = nullptr;                           // its distance map (large grids only)
+    // K7 trace_pool: per-sample hit records (tri, t, u, v) of this device's strips, read back by K1 <kVariantFromHits>
+    uint32_t *d_pool_tri = nullptr;
+    float *d_pool_t = nullptr, *d_pool_u = nullptr, *d_pool_v = nullptr;
+    uint64_t pool_cap = 0;
+    int resolve_blocks_per_sm = 0, resolve_threads = 0;
     float4 *d_cell_tris = nullptr, *d_cell_tris_b = nullptr, *d_tri_normals = nullptr;
     uint32_t *d_ppair_start = nullptr;  // padded CSR of the pair records (rt_device.cuh)
     float4 *d_pair_recs = nullptr;      // two triangles per record, interleaved: the packed-fp32 test of K1
@@ -92,7 +98,8 @@ struct Tuning
 {
     int strip_pixels = 0;  // RTM_STRIP_PIXELS = 2 | 4 | 8 | 16 | 32 pixels per strip (0: by sample count)
     int split_parts = 0;   // RTM_SPLIT_PARTS = 1 | 2 pieces per expensive strip (0: by strip size)
-    int occ_mode = -1;     // RTM_OCC_MODE = 0 | 1 | 2 home of the occupancy map (-1: by grid size)
+    int occ_mode = -1;     // RTM_OCC_MODE = 0 | 1 | 2 | 3 home of the occupancy map (-1: by grid size)
+    int pool = -1;         // RTM_POOL = 0 | 1 pooled-ray traversal K7 for the frames it supports (-1: grids with a distance map)
     int threads = 0;       // RTM_THREADS = CTA size (0: by frame size)
     int band_flush = 0;    // RTM_BAND_FLUSH = 1..8 strips a warp holds before publishing (0: by frame size)
     int shard_chunk = 0;   // RTM_SHARD_CHUNK = strips per deal when sharding (0: 32)
@@ -213,8 +220,8 @@ void free_scene(DeviceState& d)
     cudaFree(d.d_ppair_start); cudaFree(d.d_pair_recs); cudaFree(d.d_pair_recs_rel);
     d.d_ppair_start = nullptr; d.d_pair_recs = nullptr; d.d_pair_recs_rel = nullptr;
     d.rel_valid = false;
-    cudaFree(d.d_pcell_start); cudaFree(d.d_pcell_occ);
-    d.d_pcell_start = nullptr; d.d_pcell_occ = nullptr;
+    cudaFree(d.d_pcell_start); cudaFree(d.d_pcell_occ); cudaFree(d.d_pcell_dist);
+    d.d_pcell_start = nullptr; d.d_pcell_occ = nullptr; d.d_pcell_dist = nullptr;
     d.d_vtx = nullptr; d.d_tri = nullptr; d.d_cell_start = nullptr; d.d_cell_occ = nullptr;
     d.d_tri_index = nullptr; d.d_cell_tris = nullptr; d.d_cell_tris_b = nullptr; d.d_tri_normals = nullptr;
 }
@@ -234,6 +241,7 @@ GridDev grid_dev(const cuda_trace_ctx *ctx, const DeviceState& d)
     g.cell_occ = d.d_cell_occ;
     g.pcell_start = d.d_pcell_start;
     g.pcell_occ = d.d_pcell_occ;
+    g.pcell_dist = d.d_pcell_dist;
     g.cell_tris = d.d_cell_tris;
     g.cell_tris_b = d.d_cell_tris_b;
     g.ppair_start = d.d_ppair_start;
@@ -243,6 +251,10 @@ GridDev grid_dev(const cuda_trace_ctx *ctx, const DeviceState& d)
     g.tri = d.d_tri;
     return g;
 }
+
+// shared memory the staged occupancy map may take (next to the sample table) when the launcher chooses by itself
+constexpr uint64_t kOccSmemBudget = 160 * 1024;
+inline uint64_t occupancy_bits_bytes(uint64_t pcells) { return (pcells + 31) / 32 * 4; }
 
 // After d_vtx / d_tri / d_cell_start / d_tri_index are in place on device d: derived layout
 int finish_scene_on_device(cuda_trace_ctx *ctx, DeviceState& d)
@@ -262,6 +274,13 @@ int finish_scene_on_device(cuda_trace_ctx *ctx, DeviceState& d)
     launch_cell_occupancy(d.d_cell_start, cells, d.d_cell_occ, d.stream);
     launch_pad_grid(d.d_cell_start, ctx->desc.dim, d.d_pcell_start, d.d_pcell_occ, d.stream);
     ctx->launches += 2;
+    // grids whose occupancy bits do not fit in shared memory (choose_cta) get the distance map as a second level
+    if (occupancy_bits_bytes(pcells) > kOccSmemBudget || ctx->tune.occ_mode == kOccGlobalDist || ctx->tune.pool == 1)
+    {
+        CK(cudaMalloc(&d.d_pcell_dist, pcells));
+        launch_distance_map(d.d_pcell_occ, ctx->desc.dim, d.d_pcell_dist, d.stream);
+        ctx->launches += 3;
+    }
     launch_pack_cell_tris(d.d_vtx, d.d_tri, d.d_tri_index, refs, d.d_cell_tris, d.d_cell_tris_b, d.stream);
     launch_pack_normals(d.d_vtx, d.d_tri, ctx->num_tri, d.d_tri_normals, d.stream);
     ctx->launches += 2 + (refs ? 1 : 0);
@@ -524,7 +543,9 @@ int cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **
     if (const char *e = std::getenv("RTM_SPLIT_PARTS"))
         ctx->tune.split_parts = (std::atoi(e) == 1 || std::atoi(e) == 2) ? std::atoi(e) : 0;
     if (const char *e = std::getenv("RTM_OCC_MODE"))
-        ctx->tune.occ_mode = (std::atoi(e) >= 0 && std::atoi(e) <= 2) ? std::atoi(e) : -1;
+        ctx->tune.occ_mode = (std::atoi(e) >= 0 && std::atoi(e) <= 3) ? std::atoi(e) : -1;
+    if (const char *e = std::getenv("RTM_POOL"))
+        ctx->tune.pool = std::atoi(e) != 0 ? 1 : 0;
     if (const char *e = std::getenv("RTM_THREADS"))
     {
         const int t = std::atoi(e);
@@ -574,6 +595,7 @@ void cuda_trace_destroy(cuda_trace_ctx *ctx)
     {
         free_scene(d);
         cudaFree(d.d_smp); cudaFree(d.d_tile_rects); cudaFree(d.d_tile_prefix); cudaFree(d.d_strip_counter);
+        cudaFree(d.d_pool_tri); cudaFree(d.d_pool_t); cudaFree(d.d_pool_u); cudaFree(d.d_pool_v);
         cudaFreeHost(d.h_cancel_seen); cudaFree(d.d_counters);
         cudaFree(d.d_strip_cycles); cudaFree(d.d_fetch_order); cudaFree(d.d_cost_sum); cudaFree(d.d_order_scratch);
         cudaFree(d.d_visit_total); cudaFree(d.d_visit_cycles);
@@ -747,6 +769,25 @@ int cuda_trace_download_grid(cuda_trace_ctx *ctx, cuda_trace_grid_desc *desc, ui
     {
         CK(cudaMemcpyAsync(tri_index, d.d_tri_index, ctx->desc.num_refs * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                            d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+    }
+    return 0;
+}
+
+int cuda_trace_download_distance_map(cuda_trace_ctx *ctx, uint8_t *out, uint64_t *num_bytes)
+{
+    if (!ctx || !num_bytes)
+        return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
+    if (!ctx->have_scene)
+        return fail(ctx, CUDA_TRACE_ERR_NO_SCENE, "download_distance_map: no scene uploaded");
+    DeviceState& d = ctx->dev[0];
+    const uint64_t pcells = (uint64_t) (ctx->desc.dim[0] + 2) * (ctx->desc.dim[1] + 2) * (ctx->desc.dim[2] + 2);
+    *num_bytes = d.d_pcell_dist ? pcells : 0;
+    if (out && d.d_pcell_dist)
+    {
+        CK(cudaSetDevice(d.ordinal));
+        CK(cudaMemcpyAsync(out, d.d_pcell_dist, pcells, cudaMemcpyDeviceToHost, d.stream));
         CK(cudaStreamSynchronize(d.stream));
     }
     return 0;
@@ -1065,8 +1106,11 @@ int choose_cta(const cuda_trace_ctx *ctx, const DeviceState& d, const cuda_trace
             p.occ_smem_words = (uint32_t) bit_words;
         }
     }
+    if (p.occ_mode == kOccGlobalBits && d.d_pcell_dist && ctx->tune.occ_mode < 0)
+        p.occ_mode = kOccGlobalDist; // too large for shared memory: distance map through L1
     const int m = ctx->tune.occ_mode;
     if (m == kOccGlobalBits) { p.occ_mode = kOccGlobalBits; p.occ_smem_words = 0; }
+    if (m == kOccGlobalDist && d.d_pcell_dist) { p.occ_mode = kOccGlobalDist; p.occ_smem_words = 0; }
     if (m == kOccSmemBits && bit_words * 4 + smp_bytes <= 200 * 1024) { p.occ_mode = kOccSmemBits; p.occ_smem_words = (uint32_t) bit_words; }
     if (m == kOccSmemBytes && byte_words * 4 + smp_bytes <= 200 * 1024) { p.occ_mode = kOccSmemBytes; p.occ_smem_words = (uint32_t) byte_words; }
     if (ctx->tune.threads)
@@ -1082,7 +1126,7 @@ int choose_cta(const cuda_trace_ctx *ctx, const DeviceState& d, const cuda_trace
 // Cost order from the previous frame (schedule.cu), valid only if that frame had the same layout and shard.
 // Worth its ~1 % instrumentation cost when the frame is sharded or small (the tail of expensive strips is then a
 // large part of the launch); RTM_COST_ORDER=0/1 forces it
-int prepare_cost_order(cuda_trace_ctx *ctx, DeviceState& d, const cuda_trace_frame *f, TraceParams& p)
+int prepare_cost_order(cuda_trace_ctx *ctx, DeviceState& d, const cuda_trace_frame *f, TraceParams& p, bool use_pool)
 {
     const FramePlan& pl = ctx->plan;
     const uint32_t shard_strips = p.shard_strips;
@@ -1091,7 +1135,7 @@ int prepare_cost_order(cuda_trace_ctx *ctx, DeviceState& d, const cuda_trace_fra
     p.visit_total = nullptr;
     const bool want_order = (ctx->cost_order_forced >= 0 ? ctx->cost_order_forced != 0
                             : (p.shard_world > 1 || (uint64_t) f->width * f->height * f->spp < (64ull << 20))) &&
-                            shard_strips <= kVisitStripMask;
+                            shard_strips <= kVisitStripMask && !use_pool; // (K7 balances by pooling, not by order)
     if (!want_order || shard_strips == 0)
     {
         d.order_valid = false;
@@ -1219,7 +1263,13 @@ int launch_on_device(cuda_trace_ctx *ctx, uint32_t i, const cuda_trace_frame *f,
         const uint64_t my_chunks = (chunks_total + p.shard_world - 1) / p.shard_world;
         p.shard_strips = (uint32_t) (my_chunks * p.shard_chunk); // (< 2^32: checked by the caller)
     }
-    int rc = prepare_cost_order(ctx, d, f, p);
+    // K7 trace_pool (pool_trace.cu) does the traversal when rays are incoherent: grids with a distance map, i.e. too
+    // large for a shared-memory occupancy map.  Primary rays of the perspective camera, Moeller-Trumbore, no work
+    // counters; RTM_POOL=0/1 forces it off / on wherever it is supported
+    const bool use_pool = d.d_pcell_dist && ctx->tune.pool != 0 && !kind.alternates && !kind.count_inst &&
+                          f->variant == kVariantMT && f->spp <= 32 && ctx->num_pairs > 0 &&
+                          (uint64_t) f->width * f->height * f->spp < (1ull << 32);
+    int rc = prepare_cost_order(ctx, d, f, p, use_pool);
     if (rc)
         return rc;
 
@@ -1270,7 +1320,43 @@ int launch_on_device(cuda_trace_ctx *ctx, uint32_t i, const cuda_trace_frame *f,
         }
         p.grid.pair_recs_rel = d.d_pair_recs_rel;
     }
-    if (pl.total)
+    if (pl.total && use_pool)
+    {
+        // hit records: the caller's (KEEP_HITS, device 0) or this device's own
+        TraceParams pp = p;
+        if (!kind.keep_hits)
+        {
+            const uint64_t need = (uint64_t) f->width * f->height * f->spp;
+            if (d.pool_cap < need)
+            {
+                cudaFree(d.d_pool_tri); cudaFree(d.d_pool_t); cudaFree(d.d_pool_u); cudaFree(d.d_pool_v);
+                d.d_pool_tri = nullptr; d.d_pool_t = d.d_pool_u = d.d_pool_v = nullptr;
+                d.pool_cap = 0;
+                CK(cudaMalloc(&d.d_pool_tri, need * 4));
+                CK(cudaMalloc(&d.d_pool_t, need * 4));
+                CK(cudaMalloc(&d.d_pool_u, need * 4));
+                CK(cudaMalloc(&d.d_pool_v, need * 4));
+                d.pool_cap = need;
+            }
+            pp.hit_tri = d.d_pool_tri; pp.hit_t = d.d_pool_t; pp.hit_u = d.d_pool_u; pp.hit_v = d.d_pool_v;
+        }
+        // K7: one CTA per SM at 1024 threads (64 registers), more of the smaller CTAs of small frames
+        const int pool_blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) d.sm_count * std::max(1, 1024 / threads), want));
+        launch_trace_pool(pp, pool_blocks, threads, d.stream);
+        // K1 behind it: shading, in-order sample sum, resolve, band publication -- from the hit records
+        pp.occ_mode = kOccGlobalBits;
+        pp.occ_smem_words = 0;
+        if (d.resolve_threads != threads)
+        {
+            d.resolve_blocks_per_sm = std::max(1, trace_tiles_max_blocks_per_sm(kVariantFromHits, false, false, kOccGlobalBits, threads,
+                                                                              trace_tiles_smem_bytes(f->spp, 0)));
+            d.resolve_threads = threads;
+        }
+        const int resolve_blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) d.sm_count * d.resolve_blocks_per_sm, want));
+        launch_trace_tiles(pp, kVariantFromHits, false, false, resolve_blocks, threads, d.stream);
+        ctx->launches += 2;
+    }
+    else if (pl.total)
     {
         launch_trace_tiles(p, kvariant, kind.keep_hits, kind.count_inst, blocks, threads, d.stream);
         ctx->launches++;

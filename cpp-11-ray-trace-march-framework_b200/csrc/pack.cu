@@ -129,6 +129,57 @@ __global__ void pad_cell_occ_kernel(const uint32_t *__restrict__ pcell_start, ui
     pcell_occ[w] = bits;
 }
 
+// ---- distance map over the padded grid (second level of the empty-space walk, warp_trace.cuh kOccGlobalDist):
+// dist[q] = min(255, city-block distance in cells from padded cell q to the nearest cell whose occupancy bit is
+// set -- a non-empty cell or a border cell).  A DDA step moves to a face neighbour, so a ray standing on a cell of
+// distance v meets only empty cells during its next v - 1 steps, whatever its direction: those steps need no
+// look-up at all.  The city-block transform is separable: one forward / backward sweep per axis is exact.
+__global__ void dist_sweep_x_kernel(const uint32_t *__restrict__ pcell_occ, uint32_t pdx, uint64_t lines, uint8_t *__restrict__ dist)
+{
+    const uint64_t line = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= lines)
+        return;
+    const uint64_t q0 = line * pdx;
+    uint32_t d = 255;
+    for (uint32_t x = 0; x < pdx; x++)
+    {
+        const uint64_t q = q0 + x;
+        const bool set = (pcell_occ[q >> 5] >> (q & 31)) & 1u;
+        d = set ? 0u : min(d + 1u, 255u);
+        dist[q] = (uint8_t) d;
+    }
+    for (uint32_t x = pdx; x-- > 0;)
+    {
+        const uint64_t q = q0 + x;
+        d = min((uint32_t) dist[q], min(d + 1u, 255u));
+        dist[q] = (uint8_t) d;
+    }
+}
+
+// sweep along an axis whose cell stride is `stride`; thread t handles the line starting at
+// (t % inner) + (t / inner) * outer_stride (neighbouring threads = neighbouring x: coalesced)
+__global__ void dist_sweep_kernel(uint8_t *__restrict__ dist, uint32_t n, uint64_t stride, uint32_t inner, uint64_t outer_stride,
+                                  uint64_t lines)
+{
+    const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= lines)
+        return;
+    const uint64_t q0 = (t % inner) + (t / inner) * outer_stride;
+    uint32_t d = 255;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        const uint64_t q = q0 + i * stride;
+        d = min((uint32_t) dist[q], min(d + 1u, 255u));
+        dist[q] = (uint8_t) d;
+    }
+    for (uint32_t i = n; i-- > 0;)
+    {
+        const uint64_t q = q0 + i * stride;
+        d = min((uint32_t) dist[q], min(d + 1u, 255u));
+        dist[q] = (uint8_t) d;
+    }
+}
+
 __global__ void narrow_offsets_kernel(const uint64_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out)
 {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -285,6 +336,16 @@ void launch_pad_grid(const uint32_t *cell_start, const uint32_t dim[3], uint32_t
     const uint64_t pcells = (uint64_t) (dim[0] + 2) * (dim[1] + 2) * (dim[2] + 2);
     pad_cell_start_kernel<<<blocks_for(pcells + 1, 256), 256, 0, stream>>>(cell_start, dim[0], dim[1], dim[2], pcell_start);
     pad_cell_occ_kernel<<<blocks_for((pcells + 31) / 32, 256), 256, 0, stream>>>(pcell_start, dim[0], dim[1], dim[2], pcell_occ);
+}
+
+void launch_distance_map(const uint32_t *pcell_occ, const uint32_t dim[3], uint8_t *pcell_dist, cudaStream_t stream)
+{
+    const uint32_t pdx = dim[0] + 2, pdy = dim[1] + 2, pdz = dim[2] + 2;
+    const uint64_t plane = (uint64_t) pdx * pdz;
+    // x: one thread per (z, y) line; z: one per (x, y), lines start at x + y * plane; y: one per (x, z), start x + z * pdx
+    dist_sweep_x_kernel<<<blocks_for((uint64_t) pdz * pdy, 128), 128, 0, stream>>>(pcell_occ, pdx, (uint64_t) pdz * pdy, pcell_dist);
+    dist_sweep_kernel<<<blocks_for((uint64_t) pdx * pdy, 128), 128, 0, stream>>>(pcell_dist, pdz, pdx, pdx, plane, (uint64_t) pdx * pdy);
+    dist_sweep_kernel<<<blocks_for(plane, 128), 128, 0, stream>>>(pcell_dist, pdy, plane, (uint32_t) plane, 0, plane);
 }
 
 void launch_narrow_offsets(const uint64_t *off64, uint64_t n, uint32_t *off32, cudaStream_t stream)

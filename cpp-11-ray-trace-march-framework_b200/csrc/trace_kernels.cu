@@ -27,27 +27,44 @@ template <int VARIANT, bool KEEP_HITS, bool COUNT, int OCC_MODE, bool RCP_GUARD>
 __device__ __forceinline__ float3 trace_sample(const TraceParams& p, const void *s_occ, bool valid,
                                                uint32_t px, uint32_t py, uint32_t s, const float2 *smp, Counters *cnt)
 {
-    float3 o, d;
-    const float2 off = smp[valid ? s : 0];
-    constexpr bool ALT = VARIANT >= kVariantMTAlt;
+    constexpr bool FROM_HITS = VARIANT == kVariantFromHits;
+    constexpr bool ALT = VARIANT >= kVariantMTAlt && !FROM_HITS;
     constexpr int TRI_VARIANT = ALT ? VARIANT - kVariantMTAlt : VARIANT;
-    generate_ray<ALT>(p.cam, px, py, off.x, off.y, o, d);
     Hit hit;
     hit.t = hit.u = hit.v = 0.0f;
     hit.tri = 0xFFFFFFFFu;
-    if (COUNT && valid) cnt->rays++;
-    PackedUnits pku;
-    pku.one = p.pk_one;
-    pku.minus_one = p.pk_minus_one;
-    const bool is_hit = warp_grid_intersect<TRI_VARIANT, COUNT, OCC_MODE, RCP_GUARD>(p.grid, s_occ, o, d, valid, hit, cnt, pku, p.cam.fast_math != 0);
-    if (COUNT && is_hit) cnt->hits++;
-    if (KEEP_HITS && valid)
+    bool is_hit = false;
+    if constexpr (FROM_HITS)
     {
-        const size_t k = ((size_t) py * p.width + px) * p.spp + s;
-        p.hit_tri[k] = is_hit ? hit.tri : 0xFFFFFFFFu;
-        if (p.hit_t) p.hit_t[k] = is_hit ? hit.t : 0.0f;
-        if (p.hit_u) p.hit_u[k] = is_hit ? hit.u : 0.0f;
-        if (p.hit_v) p.hit_v[k] = is_hit ? hit.v : 0.0f;
+        // the traversal was done by K7 trace_pool (pool_trace.cu): take the sample's hit record as it left it
+        if (valid)
+        {
+            const size_t k = ((size_t) py * p.width + px) * p.spp + s;
+            hit.tri = p.hit_tri[k];
+            hit.u = p.hit_u[k];
+            hit.v = p.hit_v[k];
+            is_hit = hit.tri != 0xFFFFFFFFu;
+        }
+    }
+    else
+    {
+        float3 o, d;
+        const float2 off = smp[valid ? s : 0];
+        generate_ray<ALT>(p.cam, px, py, off.x, off.y, o, d);
+        if (COUNT && valid) cnt->rays++;
+        PackedUnits pku;
+        pku.one = p.pk_one;
+        pku.minus_one = p.pk_minus_one;
+        is_hit = warp_grid_intersect<TRI_VARIANT, COUNT, OCC_MODE, RCP_GUARD>(p.grid, s_occ, o, d, valid, hit, cnt, pku, p.cam.fast_math != 0);
+        if (COUNT && is_hit) cnt->hits++;
+        if (KEEP_HITS && valid)
+        {
+            const size_t k = ((size_t) py * p.width + px) * p.spp + s;
+            p.hit_tri[k] = is_hit ? hit.tri : 0xFFFFFFFFu;
+            if (p.hit_t) p.hit_t[k] = is_hit ? hit.t : 0.0f;
+            if (p.hit_u) p.hit_u[k] = is_hit ? hit.u : 0.0f;
+            if (p.hit_v) p.hit_v[k] = is_hit ? hit.v : 0.0f;
+        }
     }
     float3 rgb = make_float3(0.0f, 0.0f, 0.0f);
     if (valid)
@@ -501,6 +518,8 @@ void launch_one(const TraceParams& p, int grid_blocks, int threads, cudaStream_t
         launch_mode<VARIANT, KEEP_HITS, COUNT, kOccSmemBytes>(p, grid_blocks, threads, smem, stream);
     else if (p.occ_mode == kOccSmemBits)
         launch_mode<VARIANT, KEEP_HITS, COUNT, kOccSmemBits>(p, grid_blocks, threads, smem, stream);
+    else if (p.occ_mode == kOccGlobalDist)
+        launch_mode<VARIANT, KEEP_HITS, COUNT, kOccGlobalDist>(p, grid_blocks, threads, smem, stream);
     else
         launch_mode<VARIANT, KEEP_HITS, COUNT, kOccGlobalBits>(p, grid_blocks, threads, smem, stream);
 }
@@ -523,6 +542,8 @@ int occupancy_one(int occ_mode, int threads, size_t smem)
         return occupancy_mode<VARIANT, KEEP_HITS, COUNT, kOccSmemBytes>(threads, smem);
     if (occ_mode == kOccSmemBits)
         return occupancy_mode<VARIANT, KEEP_HITS, COUNT, kOccSmemBits>(threads, smem);
+    if (occ_mode == kOccGlobalDist)
+        return occupancy_mode<VARIANT, KEEP_HITS, COUNT, kOccGlobalDist>(threads, smem);
     return occupancy_mode<VARIANT, KEEP_HITS, COUNT, kOccGlobalBits>(threads, smem);
 }
 
@@ -540,6 +561,7 @@ int occupancy_one(int occ_mode, int threads, size_t smem)
             case 14: case 15: return FN<3, true, false>(__VA_ARGS__);                            \
             case 16: case 17: return FN<4, false, false>(__VA_ARGS__);                           \
             case 18: case 19: return FN<4, true, false>(__VA_ARGS__);                            \
+            case 20: case 21: case 22: case 23: return FN<5, false, false>(__VA_ARGS__);         \
             case 0: return FN<0, false, false>(__VA_ARGS__);                                     \
             case 1: return FN<0, false, true>(__VA_ARGS__);                                      \
             case 2: return FN<0, true, false>(__VA_ARGS__);                                      \

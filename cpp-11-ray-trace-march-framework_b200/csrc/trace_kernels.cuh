@@ -36,13 +36,22 @@ constexpr int kTraceMaxThreads = 1024; // launch bound (caps the kernel at 64 re
 //   1  bits staged in shared memory                      (<= ~1.6 M padded cells)
 //   2  one BYTE per cell in shared memory                (<= ~220 K padded cells, i.e. the res-64
 //      grids of configs C2-C4): the test is a single LDS.U8 without shift / mask arithmetic
-enum { kOccGlobalBits = 0, kOccSmemBits = 1, kOccSmemBytes = 2 };
+//   3  distance map in global memory, read through L1   (grids too large for 1 / 2): one byte per cell holding the
+//      city-block distance to the nearest occupied cell -- a ray steps that many cells between look-ups
+enum { kOccGlobalBits = 0, kOccSmemBits = 1, kOccSmemBytes = 2, kOccGlobalDist = 3 };
 
 // Kernel-side intersection variants: 0 / 1 are the ABI's (Moeller-Trumbore, plane + barycentric); 2 is
 // Moeller-Trumbore on origin-relative records (GridDev::pair_recs_rel) -- the launcher's choice for primary rays
 // 3 / 4 are 0 / 1 with the reference's alternates compiled in (orthographic camera, face-normal and depth shading:
 // CameraDev::ortho, TraceParams::shade_mode) -- separate instantiations so that the live path does not carry them
-enum { kVariantMT = 0, kVariantBary = 1, kVariantMTRel = 2, kVariantMTAlt = 3, kVariantBaryAlt = 4 };
+// 5 does not traverse at all: the hit records were written by K7 trace_pool (pool_trace.cu); K1 shades, sums, resolves
+enum { kVariantMT = 0, kVariantBary = 1, kVariantMTRel = 2, kVariantMTAlt = 3, kVariantBaryAlt = 4, kVariantFromHits = 5 };
+
+// K7 trace_pool (pool_trace.cu): rays per warp pool, bytes of one warp's pool in shared memory, and the word of the
+// strip-counter line its scheduler counts in (word 0 is K1's, which runs behind it on the same stream)
+constexpr int kPoolSlots = 64;
+constexpr int kPoolWarpBytes = (9 + 6) * kPoolSlots * 4 + 32 * 4;
+constexpr int kPoolCounterWord = 16;
 
 struct TraceParams
 {
@@ -52,7 +61,7 @@ struct TraceParams
     uint32_t gamma;
     uint32_t shade_mode;               // 0 interpolated vertex normal (live), 1 face normal, 2 depth (rt_device.cuh)
     const float2 *smp;                 // sample table, spp entries (K2)
-    uint32_t occ_mode;                 // kOccGlobalBits / kOccSmemBits / kOccSmemBytes (warp_trace.cuh)
+    uint32_t occ_mode;                 // kOccGlobalBits / kOccSmemBits / kOccSmemBytes / kOccGlobalDist (warp_trace.cuh)
     uint32_t occ_smem_words;           // 32-bit words of the occupancy map staged in shared memory
     uint32_t rcp_guard;                // 1: the scene extent allows |det| > 1e30, keep rcp_exact's range check
     const uint4 *tile_rects;           // n_tiles x {x0,y0,x1,y1}
@@ -103,6 +112,10 @@ void launch_trace_tiles(const TraceParams& p, uint32_t variant, bool keep_hits, 
 int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count, int occ_mode, int threads,
                                   size_t smem_bytes);
 size_t trace_tiles_smem_bytes(uint32_t spp, uint32_t occ_smem_words);
+// K7: traverses the strips of this launch's shard with pooled rays and leaves (tri, t, u, v) per sample in p.hit_*
+// (all four required); follow it with launch_trace_tiles(variant = kVariantFromHits) on the same stream
+void launch_trace_pool(const TraceParams& p, int grid_blocks, int threads, cudaStream_t stream);
+size_t trace_pool_smem_bytes(uint32_t spp, int threads);
 void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, cudaStream_t stream);
 void launch_sample_table(float2 *smp, uint32_t spp, cudaStream_t stream);
 void launch_ray_march(const float *vtx, const uint32_t *tri, uint32_t num_tri, uint32_t n, const float *origins,
@@ -132,6 +145,7 @@ void launch_pack_normals(const float *vtx, const uint32_t *tri, uint32_t num_tri
 void launch_cell_occupancy(const uint32_t *cell_start, uint64_t num_cells, uint32_t *cell_occ, cudaStream_t stream);
 void launch_pad_grid(const uint32_t *cell_start, const uint32_t dim[3], uint32_t *pcell_start, uint32_t *pcell_occ,
                      cudaStream_t stream); // 2 kernels
+void launch_distance_map(const uint32_t *pcell_occ, const uint32_t dim[3], uint8_t *pcell_dist, cudaStream_t stream); // 3 kernels
 void launch_narrow_offsets(const uint64_t *off64, uint64_t n, uint32_t *off32, cudaStream_t stream);
 void launch_widen_offsets(const uint32_t *off32, uint64_t n, uint64_t *off64, cudaStream_t stream);
 

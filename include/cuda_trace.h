@@ -143,6 +143,15 @@ int cuda_trace_upload_scene_with_grid(cuda_trace_ctx *ctx, const float *vertices
 int cuda_trace_download_grid(cuda_trace_ctx *ctx, cuda_trace_grid_desc *desc, uint64_t *cell_offset,
                              uint32_t *tri_index);
 
+/* Second level of the empty-space walk on large grids (no counterpart in the reference; its author's TODO of a
+ * "two-level" grid, grid.h:35-36): one byte per cell of the grid PADDED by one cell on every side, padded cell
+ * (X, Y, Z) at X + Z*(dim[0]+2) + Y*(dim[0]+2)*(dim[2]+2), holding min(255, city-block distance in cells to the
+ * nearest non-empty cell or padding cell).  The 3D-DDA takes that many steps between look-ups; the cells visited
+ * and the arithmetic per step are unchanged, so results stay bit-exact.  Built with the scene whenever the
+ * occupancy bitmap of the grid does not fit in shared memory.  out == NULL: query only.  *num_bytes receives
+ * the map's size, 0 when this scene has none. */
+int cuda_trace_download_distance_map(cuda_trace_ctx *ctx, uint8_t *out, uint64_t *num_bytes);
+
 /* ---- tracing --------------------------------------------------------------------------------
  * cuda_trace_tiles replaces Framebuffer::CreateWorkerThreads + WorkerThread + RenderTile for the
  * given tiles (framebuffer.cpp:16-27,59-92; renderer.cpp:43-136): it renders every pixel of every

@@ -274,8 +274,7 @@ class _Scene(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays", "cells", "tri_tests", "hits", "rej_det", "rej_u",
-                                          "rej_v", "full", "box_miss", "rep2", "rep8", "rep64", "nonempty",
-                                          "pre_reject", "pre_violation", "pre_keep_fail")]
+                                          "rej_v", "full", "box_miss", "nonempty")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

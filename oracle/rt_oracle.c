@@ -44,9 +44,7 @@ static void cnt_add(rto_counters *dst, const rto_counters *src)
     dst->tri_tests += src->tri_tests; dst->hits += src->hits;
     dst->rej_det += src->rej_det;     dst->rej_u += src->rej_u;
     dst->rej_v += src->rej_v;         dst->full += src->full;
-    dst->box_miss += src->box_miss;
-    dst->rep2 += src->rep2; dst->rep8 += src->rep8; dst->rep64 += src->rep64; dst->nonempty += src->nonempty;
-    dst->pre_reject += src->pre_reject; dst->pre_violation += src->pre_violation; dst->pre_keep_fail += src->pre_keep_fail;
+    dst->box_miss += src->box_miss;   dst->nonempty += src->nonempty;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -545,24 +543,6 @@ static int to_voxel(const rto_grid *g, const float *p, int axis)
 static float to_pos(const rto_grid *g, int vox, int axis) { return g->aabb_min[axis] + vox * g->cell_wdh; }
 
 /* grid.cpp:159-281 */
-/* Walk recorder (scheduling studies only, tools/warp_walk_model.py): when armed, rto_grid_intersect appends the
- * triangle-list length of every cell it visits, in order */
-static __thread uint16_t *g_walk_out;
-static __thread uint32_t g_walk_cap, g_walk_n;
-
-uint32_t rto_ray_walk_profile(const rto_scene *sc, const float *origin, const float *dir, uint32_t cap,
-                              uint16_t *list_lengths, int *hit)
-{
-    float t, u, v;
-    uint32_t idx;
-    g_walk_out = list_lengths;
-    g_walk_cap = cap;
-    g_walk_n = 0;
-    *hit = rto_grid_intersect(sc, origin, dir, RTO_VARIANT_MT, &t, &u, &v, &idx, NULL);
-    g_walk_out = NULL;
-    return g_walk_n;
-}
-
 int rto_grid_intersect(const rto_scene *sc, const float *origin, const float *dir, int variant,
                        float *t, float *u, float *v, uint32_t *tri_idx, rto_counters *cnt)
 {
@@ -616,8 +596,6 @@ int rto_grid_intersect(const rto_scene *sc, const float *origin, const float *di
 
     /* :219-278 */
     *t = FLT_MAX;
-    uint32_t mbox[64];
-    uint32_t mbox_n = 0;
     for (;;)
     {
         const int sa = (next_t[0] < next_t[1]) ? ((next_t[0] < next_t[2]) ? 0 : 2)
@@ -626,28 +604,9 @@ int rto_grid_intersect(const rto_scene *sc, const float *origin, const float *di
                               (uint64_t) pos[1] * g->dim[0] * g->dim[2];
         if (cnt) cnt->cells++;
         if (cnt && g->cell_offset[cell] != g->cell_offset[cell + 1]) cnt->nonempty++;
-        if (g_walk_out)
-        {
-            const uint64_t len = g->cell_offset[cell + 1] - g->cell_offset[cell];
-            if (g_walk_n < g_walk_cap)
-                g_walk_out[g_walk_n] = (uint16_t) (len > 65535 ? 65535 : len);
-            g_walk_n++;
-        }
         for (uint64_t k = g->cell_offset[cell]; k < g->cell_offset[cell + 1]; k++)
         {
             const uint32_t ci = g->tri_index[k];
-            if (cnt)
-            {
-                /* mailbox study only: how often was this triangle already tested by this ray? */
-                int found = -1;
-                for (uint32_t m = 0; m < mbox_n && m < 64; m++)
-                    if (mbox[(mbox_n - 1 - m) & 63] == ci) { found = (int) m; break; }
-                if (found >= 0 && found < 2) cnt->rep2++;
-                if (found >= 0 && found < 8) cnt->rep8++;
-                if (found >= 0) cnt->rep64++;
-                mbox[mbox_n & 63] = ci;
-                mbox_n++;
-            }
             const uint32_t *tr = sc->tri + (size_t) ci * 6;
             const float *v0 = sc->vtx + (size_t) tr[0] * 6;
             const float *v1 = sc->vtx + (size_t) tr[1] * 6;
@@ -658,29 +617,6 @@ int rto_grid_intersect(const rto_scene *sc, const float *origin, const float *di
                 hit = rto_ray_tri_bary(origin, dir, v0, v1, v2, (const float *) (tr + 3), &ct, &cu, &cv, cnt);
             else
                 hit = rto_ray_tri(origin, dir, v0, v1, v2, &ct, &cu, &cv, cnt);
-            if (cnt && variant == RTO_VARIANT_MT)
-            {
-                /* pre-test study: |tvec x d|^2 > thresh, tvec = origin - v0, thresh = 1.01 * max(|e1|^2, |e2|^2)
-                 * + 32 ulp-scale * |tvec|^2 (the rounding error of the left side), all in fp32 without contraction */
-                const float tv[3] = { origin[0] - v0[0], origin[1] - v0[1], origin[2] - v0[2] };
-                const float e1[3] = { v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2] };
-                const float e2[3] = { v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2] };
-                const float l1 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2];
-                const float l2 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
-                const float tt = tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2];
-                const float thresh = (l1 > l2 ? l1 : l2) * 1.01f + tt * (32.0f * 5.9604645e-8f);
-                const float qx = tv[1] * dir[2] - tv[2] * dir[1];
-                const float qy = tv[2] * dir[0] - tv[0] * dir[2];
-                const float qz = tv[0] * dir[1] - tv[1] * dir[0];
-                const float s = qx * qx + qy * qy + qz * qz;
-                if (s > thresh)
-                {
-                    cnt->pre_reject++;
-                    if (hit) cnt->pre_violation++;
-                }
-                else if (!hit)
-                    cnt->pre_keep_fail++;
-            }
             if (hit && ct < *t && ct < next_t[sa])
             {
                 *t = ct; *u = cu; *v = cv; *tri_idx = ci;

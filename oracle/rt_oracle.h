@@ -55,15 +55,7 @@ typedef struct rto_counters
     uint64_t rej_v;      /* ... at the v stage                              */
     uint64_t full;       /* tests that computed t                           */
     uint64_t box_miss;   /* rays that missed the grid's box                 */
-    uint64_t rep2;       /* tests whose triangle was among the previous 2 tests' cells' ids (mailbox study) */
-    uint64_t rep8;       /* ... among the last 8 distinct ids tested by this ray */
-    uint64_t rep64;      /* ... among the last 64 */
     uint64_t nonempty;   /* visited cells with a non-empty list */
-    /* pre-test study: a conservative reject in front of the ray/triangle test -- the ray
-     * line's squared distance from v0 against (max edge length from v0)^2 with safety margins, in fp32 */
-    uint64_t pre_reject;      /* tests the pre-test would skip                                  */
-    uint64_t pre_violation;   /* ... of which the exact test reports a hit (must stay 0)        */
-    uint64_t pre_keep_fail;   /* tests the pre-test keeps and the exact test then rejects       */
 } rto_counters;
 
 enum { RTO_VARIANT_MT = 0 /* IntersectRayTri */, RTO_VARIANT_BARY = 1 /* IntersectRayTriBarycentric */ };
@@ -103,12 +95,6 @@ int  rto_tri_box_overlap(const double center[3], const double half[3], const dou
 /* a5: grid.cpp:159-281.  Returns 1 on hit */
 int rto_grid_intersect(const rto_scene *scene, const float *origin, const float *dir, int variant,
                        float *t, float *u, float *v, uint32_t *tri_idx, rto_counters *cnt);
-
-/* Scheduling studies (tools/warp_walk_model.py): the triangle-list lengths of the cells a ray visits, in order
- * (0 = empty cell); the last one is the cell of the hit when *hit.  Returns the number of cells visited (may
- * exceed cap; only cap entries are written) */
-uint32_t rto_ray_walk_profile(const rto_scene *scene, const float *origin, const float *dir, uint32_t cap,
-                              uint16_t *list_lengths, int *hit);
 
 /* a7 + a8 helpers: renderer.cpp:107-121, triangle.h:158-161, renderer.cpp:124-133, lin_alg.h:125-132 */
 void     rto_shade_hit(const rto_scene *scene, uint32_t tri_idx, float u, float v, float *rgb);

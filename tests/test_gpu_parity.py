@@ -175,15 +175,91 @@ def test_arbitrary_rays(cuda_trace, port, scene_data):
         assert (tri != 0xFFFFFFFF).sum() > 1000
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def cityblock_distance_map(occ):
+    """Exact city-block distance transform of a boolean volume (distance 0 where set), clamped to 255: the
+    separable two-sweep form per axis in numpy -- the checker of the device's distance map."""
+    d = np.where(occ, 0, 10 ** 6).astype(np.int64)
+    for axis in range(3):
+        d = np.moveaxis(d, axis, 0)
+        for i in range(1, d.shape[0]):
+            np.minimum(d[i], d[i - 1] + 1, out=d[i])
+        for i in range(d.shape[0] - 2, -1, -1):
+            np.minimum(d[i], d[i + 1] + 1, out=d[i])
+        d = np.moveaxis(d, 0, axis)
+    return np.minimum(d, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("name,res", [("tiger_soup_small", 150), ("killeroo", 200), ("cornell", 130)])
+def test_distance_map_matches_cityblock_transform(cuda_trace, port, scene_data, name, res):
+    """The second level of the empty-space walk (large grids): the device's distance map over the padded grid equals
+    the exact city-block distance to the nearest non-empty or padding cell, computed here from the ORACLE's grid."""
+    sd = scene_data(name)
+    cuda_trace.upload_scene(sd.vtx, sd.tri, res)
+    dist = cuda_trace.download_distance_map()
+    assert dist is not None
+    og = port.scene(sd.vtx, sd.tri, res, tight_ranges=True).grid()
+    dx, dy, dz = [int(v) for v in og["dim"]]
+    off = np.asarray(og["cell_offset"]).astype(np.int64)
+    occ = np.ones((dy + 2, dz + 2, dx + 2), bool)  # padding cells count as occupied
+    occ[1:-1, 1:-1, 1:-1] = (off[1:] != off[:-1]).reshape(dy, dz, dx)  # cell = x + z*dx + y*dx*dz (grid.h:41-42)
+    want = cityblock_distance_map(occ)
+    assert dist.shape == want.shape and np.array_equal(dist, want)
+    assert int(dist.max()) > 3  # there is something to skip
+
+
+def test_small_grids_have_no_distance_map(cuda_trace, scene_data):
+    sd = scene_data("cornell")
+    cuda_trace.upload_scene(sd.vtx, sd.tri, 64)
+    assert cuda_trace.download_distance_map() is None
+
+
+@pytest.mark.parametrize("threads", ["1024", "128"])
+@pytest.mark.parametrize("name,spp,res", [("killeroo", 4, 64), ("room", 16, 64), ("cornell", 1, 64), ("killeroo", 5, 96),
+                                          ("tiger_soup_small", 16, 150), ("torusknot", 32, 64)])
+def test_pooled_traversal(port, scene_data, monkeypatch, name, spp, res, threads):
+    """K7 trace_pool (pool_trace.cu): every warp keeps a pool of 64 rays and compacts, by ballot, 32 that need the
+    same kind of work (walk / test); K1 then shades from the hit records.  Same per-ray arithmetic, so hit records
+    and image must be bit-identical to the oracle -- with the caller's hit buffers (KEEP_HITS) and with the device's
+    own, on whole frames and on a ragged tile list whose strips are clipped."""
+    monkeypatch.setenv("RTM_POOL", "1")
+    monkeypatch.setenv("RTM_THREADS", threads)
+    sd = scene_data(name)
+    w, h = 250, 138
+    ct = pkg("capi").CudaTrace(1)
+    ct.upload_scene(sd.vtx, sd.tri, res)
+    assert ct.download_distance_map() is not None
+    o = port.scene(sd.vtx, sd.tri, res, tight_ranges=True).render(sd.cam16, sd.fov, w, h, spp, want_hits=True, want_tuv=True)
+    launches = ct.kernel_launches()
+    f = frame_for(ct, port, sd, w, h, spp, keep_hits=True)
+    img = ct.trace_tiles(f)
+    assert ct.kernel_launches() - launches == 3  # sample table + K7 + K1 <from hits>
+    tri, t, u, v = ct.download_hits(w, h, spp)
+    assert np.array_equal(tri, o["tri"])
+    for a, b in ((t, o["t"]), (u, o["u"]), (v, o["v"])):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.array_equal(img, o["bgra"])
+    # the device's own hit records + ragged tiles (pixels outside them stay untouched)
+    f2 = frame_for(ct, port, sd, w, h, spp)
+    assert np.array_equal(ct.trace_tiles(f2), o["bgra"])
+    rects = [(3, 5, 117, 61), (117, 5, 250, 61), (0, 70, 250, 138)]
+    out = np.full((h, w), 0xDEADBEEF, np.uint32)
+    got = ct.trace_tiles(f2, rects=rects, out=out)
+    want = np.full((h, w), 0xDEADBEEF, np.uint32)
+    for x0, y0, x1, y1 in rects:
+        want[y0:y1, x0:x1] = o["bgra"][y0:y1, x0:x1]
+    assert np.array_equal(got, want)
+    ct.close()
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2", "3"])
 @pytest.mark.parametrize("name,spp", [("killeroo", 4), ("room", 16), ("cornell", 1)])
 def test_occupancy_map_modes(port, scene_data, monkeypatch, mode, name, spp):
-    """The three homes of the padded occupancy map (bits through L1 / bits in shared memory / one byte
-    per cell in shared memory with the DDA tracking the byte address) and both phase-A forms must give
-    the same bits.  Small frames default to mode 0, so the shared-memory modes are forced here (the tuning
+    """The homes of the padded occupancy map (bits through L1 / bits in shared memory / one byte
+    per cell in shared memory with the DDA tracking the byte address / the distance map through L1 with look-ups
+    only every `distance` steps) and both phase-A forms must give the same bits.  Small frames default to mode 0, so the shared-memory modes are forced here (the tuning
     switches are read when a context is created)."""
     monkeypatch.setenv("RTM_OCC_MODE", mode)
-    monkeypatch.setenv("RTM_THREADS", "1024" if mode != "0" else "256")
+    monkeypatch.setenv("RTM_THREADS", "1024" if mode in ("1", "2") else "256")
     sd = scene_data(name)
     w, h = 256, 144
     cuda_trace = pkg("capi").CudaTrace(1)

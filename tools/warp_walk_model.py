@@ -1,7 +1,7 @@
 """CPU model of K1's warp-level traversal (no GPU): where do the lanes of a warp wait?
 
 For a sample of strips of a frame, the oracle port records for every primary ray the triangle-list lengths of the
-cells it visits (oracle rto_ray_walk_profile).  The model then replays K1's two-phase loop per warp round (32 rays,
+cells it visits (tools/study/rt_study.c rts_ray_walk_profile, a study copy of the oracle's walk).  The model then replays K1's two-phase loop per warp round (32 rays,
 lane = pixel-in-round * spp + sample): phase A costs the LONGEST empty-cell run among the lanes, phase B the LONGEST
 list, and compares with (a) the useful work, i.e. perfect packing, and (b) re-pairing the strip's rays between phases
 (the rays of one strip pooled, sorted by what they need next, and dealt to the strip's warps).
@@ -34,8 +34,12 @@ port = pyoracle.Port.get()
 ps = port.scene(vtx, tri, res)
 lib = port.lib
 F, U16 = C.POINTER(C.c_float), C.POINTER(C.c_uint16)
-lib.rto_ray_walk_profile.restype = C.c_uint32
-lib.rto_ray_walk_profile.argtypes = [C.c_void_p, F, F, C.c_uint32, U16, C.POINTER(C.c_int)]
+import subprocess  # noqa: E402
+STUDY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "study")
+subprocess.check_call(["bash", os.path.join(STUDY, "build.sh")])
+study = C.CDLL(os.path.join(STUDY, "librt_study.so"))
+study.rts_ray_walk_profile.restype = C.c_uint32
+study.rts_ray_walk_profile.argtypes = [C.c_void_p, F, F, C.c_uint32, U16, C.POINTER(C.c_int)]
 smp = port.sample_table(spp)
 fov_xs, aspect = port.camera_constants(fov, w, h)
 cam32 = np.ascontiguousarray(cam, np.float32)
@@ -49,7 +53,7 @@ def ray_profile(px, py, s):
     lib.rto_generate_ray(cam32.ctypes.data_as(F), px, py, w, h, float(smp[s, 0]), float(smp[s, 1]), float(fov_xs),
                          float(aspect), o.ctypes.data_as(F), d.ctypes.data_as(F))
     hit = C.c_int(0)
-    n = lib.rto_ray_walk_profile(C.byref(ps.s), o.ctypes.data_as(F), d.ctypes.data_as(F), len(prof_buf),
+    n = study.rts_ray_walk_profile(C.byref(ps.s), o.ctypes.data_as(F), d.ctypes.data_as(F), len(prof_buf),
                                  prof_buf.ctypes.data_as(U16), C.byref(hit))
     return prof_buf[:min(n, len(prof_buf))].astype(np.int64).copy()
 
