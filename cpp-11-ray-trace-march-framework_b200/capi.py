@@ -70,6 +70,7 @@ SYMBOLS = {
     "cuda_trace_download_hits": (C.c_int, [C.c_void_p, _U32P, _F32P, _F32P, _F32P]),
     "cuda_trace_intersect_rays": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, C.c_uint32, _U32P, _F32P,
                                             _F32P, _F32P]),
+    "cuda_trace_mailbox_stats": (C.c_int, [C.c_void_p, _U64P, _U64P]),
     "cuda_trace_intersect_rays_brute_force": (C.c_int, [C.c_void_p, C.c_uint32, _F32P, _F32P, _U32P, _F32P, _F32P, _F32P]),
     "cuda_trace_band_shares": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                          _U32P, _U32P, _U32P, _U32P, _U32P]),
@@ -384,7 +385,14 @@ class CudaTrace:
         self._ck(self.lib.cuda_trace_download_hits(self.h, _p(tri, _U32P), _p(t, _F32P), _p(u, _F32P), _p(v, _F32P)))
         return tri, t, u, v
 
-    def intersect_rays(self, origins, dirs, variant=VARIANT_MT):
+    def mailbox_stats(self):
+        """-> (tests asked for, tests answered from the mailbox) of the last intersect_rays(..., mailbox=True)"""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.lib.cuda_trace_mailbox_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def intersect_rays(self, origins, dirs, variant=VARIANT_MT, mailbox=False):
+        variant = variant | (0x100 if mailbox else 0)
         o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
         d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
         n = len(o)

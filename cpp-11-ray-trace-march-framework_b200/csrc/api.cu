@@ -100,6 +100,8 @@ struct Tuning
     int split_parts = 0;   // RTM_SPLIT_PARTS = 1 | 2 pieces per expensive strip (0: by strip size)
     int occ_mode = -1;     // RTM_OCC_MODE = 0 | 1 | 2 | 3 home of the occupancy map (-1: by grid size)
     int pool = -1;         // RTM_POOL = 0 | 1 pooled-ray traversal K7 for the frames it supports (-1: grids with a distance map)
+    int pool_steps = 24;   // RTM_POOL_STEPS = DDA steps per ray in one walk round of K7
+    int pool_dual = 1;     // RTM_POOL_DUAL = 0 | 1 two rays per lane in K7's walk rounds
     int threads = 0;       // RTM_THREADS = CTA size (0: by frame size)
     int band_flush = 0;    // RTM_BAND_FLUSH = 1..8 strips a warp holds before publishing (0: by frame size)
     int shard_chunk = 0;   // RTM_SHARD_CHUNK = strips per deal when sharding (0: 32)
@@ -175,6 +177,7 @@ struct cuda_trace_ctx
     int (*wait_value32)(cudaStream_t, unsigned long long, unsigned int, unsigned int) = nullptr;
 
     // per-sample hit records of the last KEEP_HITS frame (device 0)
+    unsigned long long mailbox_stats[2] = { 0, 0 }; // last mailbox run of cuda_trace_intersect_rays
     uint32_t *d_hit_tri = nullptr;
     float *d_hit_t = nullptr, *d_hit_u = nullptr, *d_hit_v = nullptr;
     uint64_t hit_cap = 0, hit_count = 0;
@@ -546,6 +549,10 @@ int cuda_trace_init_devices(const int *device_ordinals, int n, cuda_trace_ctx **
         ctx->tune.occ_mode = (std::atoi(e) >= 0 && std::atoi(e) <= 3) ? std::atoi(e) : -1;
     if (const char *e = std::getenv("RTM_POOL"))
         ctx->tune.pool = std::atoi(e) != 0 ? 1 : 0;
+    if (const char *e = std::getenv("RTM_POOL_DUAL"))
+        ctx->tune.pool_dual = std::atoi(e) != 0 ? 1 : 0;
+    if (const char *e = std::getenv("RTM_POOL_STEPS"))
+        ctx->tune.pool_steps = std::min(4096, std::max(1, std::atoi(e)));
     if (const char *e = std::getenv("RTM_THREADS"))
     {
         const int t = std::atoi(e);
@@ -688,8 +695,13 @@ int cuda_trace_upload_scene(cuda_trace_ctx *ctx, const float *vertices, uint32_t
 
 uint32_t cuda_trace_suggest_grid_res(uint32_t num_triangles)
 {
-    const double r = std::cbrt(3.0 * (double) num_triangles);
-    return (uint32_t) std::min(640.0, std::max(16.0, std::floor(r + 0.5)));
+    // ~3 cells per triangle while the occupancy map of the grid fits in shared memory (K1); grids beyond that are
+    // traversed by K7 (pooled rays, distance map), whose optimum on the soup sweep lies at ~9 cells per triangle
+    // (768^3 for 50.1 M triangles: 70.4 ms against 74.0 at 640^3 and 86.5 at 512^3)
+    double r = std::cbrt(3.0 * (double) num_triangles);
+    if (r > 108.0)
+        r = std::cbrt(9.0 * (double) num_triangles);
+    return (uint32_t) std::min(896.0, std::max(16.0, std::floor(r + 0.5)));
 }
 
 int cuda_trace_upload_scene_with_grid(cuda_trace_ctx *ctx, const float *vertices, uint32_t num_vertices,
@@ -1250,6 +1262,8 @@ int launch_on_device(cuda_trace_ctx *ctx, uint32_t i, const cuda_trace_frame *f,
     // inside this GPU's .gpu scope, so the publishing release is at system scope.  (.gpu only for RTM_FORCE_BANDS
     // runs without a reader.)
     p.band_scope_sys = ctx->two_level ? 1u : 0u;
+    p.pool_walk_steps = 0;
+    p.pool_dual = 0;
     p.hit_tri = kind.keep_hits ? ctx->d_hit_tri : nullptr;
     p.hit_t = kind.keep_hits ? ctx->d_hit_t : nullptr;
     p.hit_u = kind.keep_hits ? ctx->d_hit_u : nullptr;
@@ -1266,7 +1280,12 @@ int launch_on_device(cuda_trace_ctx *ctx, uint32_t i, const cuda_trace_frame *f,
     // K7 trace_pool (pool_trace.cu) does the traversal when rays are incoherent: grids with a distance map, i.e. too
     // large for a shared-memory occupancy map.  Primary rays of the perspective camera, Moeller-Trumbore, no work
     // counters; RTM_POOL=0/1 forces it off / on wherever it is supported
-    const bool use_pool = d.d_pcell_dist && ctx->tune.pool != 0 && !kind.alternates && !kind.count_inst &&
+    // By default only where walking dominates -- fewer than one pair record per three padded cells: on the soup sweep
+    // K7 wins at 640^3 and finer (0.25 pairs per cell and less) and loses at 512^3 and coarser (0.42 and more), where
+    // most of the time goes into long triangle lists, which coherent lanes (K1) test with broadcast loads
+    const uint64_t pcells_here = (uint64_t) (ctx->desc.dim[0] + 2) * (ctx->desc.dim[1] + 2) * (ctx->desc.dim[2] + 2);
+    const bool pool_pays = ctx->tune.pool == 1 || (uint64_t) ctx->num_pairs * 3 < pcells_here;
+    const bool use_pool = d.d_pcell_dist && ctx->tune.pool != 0 && pool_pays && !kind.alternates && !kind.count_inst &&
                           f->variant == kVariantMT && f->spp <= 32 && ctx->num_pairs > 0 &&
                           (uint64_t) f->width * f->height * f->spp < (1ull << 32);
     int rc = prepare_cost_order(ctx, d, f, p, use_pool);
@@ -1324,6 +1343,8 @@ int launch_on_device(cuda_trace_ctx *ctx, uint32_t i, const cuda_trace_frame *f,
     {
         // hit records: the caller's (KEEP_HITS, device 0) or this device's own
         TraceParams pp = p;
+        pp.pool_walk_steps = (uint32_t) ctx->tune.pool_steps;
+        pp.pool_dual = (uint32_t) ctx->tune.pool_dual;
         if (!kind.keep_hits)
         {
             const uint64_t need = (uint64_t) f->width * f->height * f->spp;
@@ -1578,12 +1599,16 @@ static int tiles_async_impl(cuda_trace_ctx *ctx, const cuda_trace_frame *f, cons
     uint32_t expected[kMaxBands];
     for (int b = 0; b < kMaxBands; b++)
         expected[b] = ctx->band_expected[b] + (use_bands && (uint32_t) b < ctx->n_bands ? ctx->band_inc[b] : 0u); // monotone across frames (wrap-safe compare)
-    // device 0 first, then its band copies, then the other devices: the copy stream is armed while the kernels start
+    // The copy stream is armed (a wait on each band counter + the band's copy) right behind the only kernel of a
+    // one-GPU context, while that kernel starts.  With several devices in one process it is armed only after EVERY
+    // device's kernel is enqueued: a device's set-up allocates, loads modules and synchronises its stream, any of which
+    // may wait for all work queued in the process -- including a copy stream that waits for counters only that device's
+    // kernel will bump.  (Armed between device 0 and device 1, a two-device context hung in its first frame.)
     for (uint32_t i = 0; i < n_dev; i++)
     {
         if ((rc = launch_on_device(ctx, i, f, kind, use_bands, seq)))
             return rc;
-        if (i == 0 && can_overlap &&
+        if (i + 1 == n_dev && can_overlap &&
             (rc = dst.tile ? enqueue_tile_copies(ctx, f, dst.tile, dst.staging, expected) : enqueue_band_copies(ctx, f, host_bgra, expected)))
             return rc;
     }
@@ -1858,7 +1883,9 @@ int cuda_trace_download_hits(cuda_trace_ctx *ctx, uint32_t *tri_idx, float *t, f
 static int intersect_rays_impl(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs, uint32_t variant,
                                bool brute_force, uint32_t *tri_idx, float *t, float *u, float *v)
 {
-    if (!ctx || (n && (!origins || !dirs || !tri_idx || !t || !u || !v)) || variant > 1)
+    const bool mailbox = (variant & CUDA_TRACE_VARIANT_MAILBOX) != 0;
+    variant &= ~CUDA_TRACE_VARIANT_MAILBOX;
+    if (!ctx || (n && (!origins || !dirs || !tri_idx || !t || !u || !v)) || variant > 1 || (mailbox && brute_force))
         return CUDA_TRACE_ERR_ARG;
     std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
     if (!ctx->have_scene)
@@ -1877,12 +1904,26 @@ static int intersect_rays_impl(cuda_trace_ctx *ctx, uint32_t n, const float *ori
     RayBatchParams p;
     p.grid = grid_dev(ctx, d);
     p.n = n; p.origins = d_o; p.dirs = d_d; p.tri = d_i; p.t = d_t; p.u = d_u; p.v = d_v;
+    p.mailbox_stats = nullptr;
+    unsigned long long *d_stats = nullptr;
+    if (mailbox)
+    {
+        CK(cudaMalloc(&d_stats, 2 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), d.stream));
+        p.mailbox_stats = d_stats;
+    }
     if (brute_force)
         launch_brute_force(d.d_vtx, d.d_tri, ctx->num_tri, p, d.stream);
     else
-        launch_intersect_rays(p, variant, d.stream);
+        launch_intersect_rays(p, variant, mailbox, d.stream);
     ctx->launches++;
     CK(cudaGetLastError());
+    if (mailbox)
+    {
+        CK(cudaMemcpyAsync(ctx->mailbox_stats, d_stats, sizeof(ctx->mailbox_stats), cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        cudaFree(d_stats);
+    }
     CK(cudaMemcpyAsync(tri_idx, d_i, (size_t) n * 4, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaMemcpyAsync(t, d_t, (size_t) n * 4, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaMemcpyAsync(u, d_u, (size_t) n * 4, cudaMemcpyDeviceToHost, d.stream));
@@ -1896,6 +1937,16 @@ int cuda_trace_intersect_rays(cuda_trace_ctx *ctx, uint32_t n, const float *orig
                               uint32_t variant, uint32_t *tri_idx, float *t, float *u, float *v)
 {
     return intersect_rays_impl(ctx, n, origins, dirs, variant, false, tri_idx, t, u, v);
+}
+
+int cuda_trace_mailbox_stats(cuda_trace_ctx *ctx, uint64_t *tests, uint64_t *reused)
+{
+    if (!ctx || !tests || !reused)
+        return CUDA_TRACE_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> guard(ctx->api_mtx);
+    *tests = ctx->mailbox_stats[0];
+    *reused = ctx->mailbox_stats[1];
+    return 0;
 }
 
 int cuda_trace_intersect_rays_brute_force(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs,

@@ -3,12 +3,13 @@
 //
 // K1 keeps a warp's 32 rays in lock step between its two phases: lanes that have reached an occupied cell wait
 // for the last walker (measured on the soup: 10.9 of 32 lanes walking, 18 of 32 threads per instruction overall).
-// Here a warp owns a POOL of 64 rays in shared memory and picks, round by round, 32 rays that all need the same
+// Here a warp owns a POOL of 96 rays in shared memory and picks, round by round, 32 rays that all need the same
 // kind of work -- the active lanes are compacted by ballot / population count across the divergent DDA walks:
 //
 //   refill  32 new rays (the next round of the warp's current strip): ray generation, grid entry, DDA set-up
-//   walk    32 rays standing in empty space step through the distance map (warp_trace.cuh, kOccGlobalDist) until
-//           they reach an occupied cell (-> test), leave the grid (-> miss) or have used their look-ups
+//   walk    32 rays standing in empty space step through the distance map (warp_trace.cuh, kOccGlobalDist), one cell
+//           per lane and iteration, until they reach an occupied cell (-> test), leave the grid (-> miss) or the
+//           round's step budget is used up
 //   test    32 rays standing on occupied cells test their cells' pair records (test_pair_list of K1, unchanged)
 //           -> hit, or back to walking
 //
@@ -29,8 +30,7 @@ namespace
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint32_t kSlotFree = 0, kSlotWalk = 1, kSlotTest = 2;
-// look-ups of the distance map a ray gets per walk round (bounds how long finished lanes wait for the longest walk)
-constexpr uint32_t kWalkLookups = 8;
+constexpr uint32_t kOwn = kPoolSlots / 32; // slots whose status a lane keeps track of: lane, lane + 32, ...
 constexpr uint32_t kMetaStepsMask = 0xFFu, kMetaNegX = 0x100u, kMetaNegY = 0x200u, kMetaNegZ = 0x400u;
 
 // One warp's pool, structure of arrays over the slots
@@ -43,19 +43,24 @@ struct PoolWarp
     uint32_t meta[kPoolSlots]; // bits 0-7: steps up to and including the next cell to look at (0: standing on a cell
                                // not looked at yet); bits 8-10: the x / y / z stride is negative
     uint32_t ray[kPoolSlots]; // index of the sample's hit record: (py * width + px) * spp + s
-    uint32_t beg[kPoolSlots], len[kPoolSlots]; // pair records of the occupied cell a tester stands on
     uint32_t status[kPoolSlots];
-    uint32_t list[32];        // the slots picked for this round, compacted
+    uint32_t list[64];        // the slots picked for this round, compacted (walk rounds take up to 64, two per lane)
 };
 static_assert(sizeof(PoolWarp) == kPoolWarpBytes, "trace_kernels.cuh: kPoolWarpBytes");
 
-// owners (lane l holds the status of slots l and l + 32) compact the slots of one kind into list[0 .. 32)
-__device__ __forceinline__ void pick_slots(PoolWarp& pw, uint32_t lane, bool mine0, bool mine1, unsigned m0, unsigned m1)
+// Compaction: the owners of the slots whose bit is set in mask[] write the slot numbers, in order, to list[0 .. 64)
+__device__ __forceinline__ void pick_slots(PoolWarp& pw, uint32_t lane, const unsigned mask[kOwn])
 {
     const unsigned lt = (1u << lane) - 1u;
-    const uint32_t r0 = __popc(m0 & lt), r1 = __popc(m0) + __popc(m1 & lt);
-    if (mine0 && r0 < 32u) pw.list[r0] = lane;
-    if (mine1 && r1 < 32u) pw.list[r1] = lane + 32u;
+    uint32_t before = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < kOwn; j++)
+    {
+        const uint32_t r = before + __popc(mask[j] & lt);
+        if (((mask[j] >> lane) & 1u) && r < 64u)
+            pw.list[r] = lane + 32u * j;
+        before += __popc(mask[j]);
+    }
     __syncwarp();
 }
 
@@ -65,6 +70,72 @@ __device__ __forceinline__ void store_miss(const TraceParams& p, uint32_t k)
     p.hit_t[k] = 0.0f;
     p.hit_u[k] = 0.0f;
     p.hit_v[k] = 0.0f;
+}
+
+// One ray of a walk round in registers
+struct Walker
+{
+    float n0, n1, n2, dl0, dl1, dl2;
+    int pc, c0, c1, c2;
+    uint32_t steps; // DDA steps up to and including the next cell to look at; 0: arrived (or no ray)
+    uint32_t meta, slot;
+    bool mine;
+};
+
+// all 32 lanes together (the x stride goes through a shuffle, the others through an opaque move: held in registers
+// instead of being re-derived from the sign bits in every step, like in K1)
+__device__ __forceinline__ void walker_load(const PoolWarp& pw, uint32_t slot, bool mine, uint32_t lane, int stride_y, int stride_z,
+                                            const uint8_t *__restrict__ dist, Walker& w)
+{
+    w.slot = slot;
+    w.mine = mine;
+    w.n0 = pw.n[0][slot]; w.n1 = pw.n[1][slot]; w.n2 = pw.n[2][slot];
+    w.dl0 = pw.dl[0][slot]; w.dl1 = pw.dl[1][slot]; w.dl2 = pw.dl[2][slot];
+    w.pc = pw.pc[slot];
+    w.meta = pw.meta[slot];
+    w.c0 = __shfl_sync(kFull, (w.meta & kMetaNegX) ? -1 : 1, (int) lane);
+    w.c1 = (w.meta & kMetaNegY) ? -stride_y : stride_y;
+    w.c2 = (w.meta & kMetaNegZ) ? -stride_z : stride_z;
+    asm volatile("" : "+r"(w.c1), "+r"(w.c2));
+    w.steps = mine ? (w.meta & kMetaStepsMask) : 0u;
+    if (mine && w.steps == 0) // standing on a cell not looked at yet
+        w.steps = cell_distance(dist, w.pc);
+}
+
+// one DDA step of a ray that still has steps to go; after the last blind one, look at the cell reached (0 = occupied
+// or padding: arrived).  (The same step with every instruction predicated on steps != 0 instead of the branch -- 48
+// instead of 52 instructions per iteration of two rays -- and L1 prefetches of the pair records ahead of the test
+// rounds were measured: 71.1 against 70.4 ms on the soup at 768^3.  Not kept.)
+__device__ __forceinline__ void walker_step(Walker& w, const uint8_t *__restrict__ dist)
+{
+    if (w.steps != 0)
+    {
+        dda_step(w.n0, w.n1, w.n2, w.dl0, w.dl1, w.dl2, w.pc, w.c0, w.c1, w.c2);
+        if (--w.steps == 0)
+            w.steps = cell_distance(dist, w.pc);
+    }
+}
+
+__device__ __forceinline__ void walker_store(const TraceParams& p, PoolWarp& pw, const uint32_t *__restrict__ pstart, const Walker& w)
+{
+    if (!w.mine)
+        return;
+    uint32_t status = kSlotWalk;
+    if (w.steps == 0)
+    {
+        // an occupied cell, or the padding: the ray has left the grid (grid.cpp:275-276)
+        if (__ldg(&pstart[w.pc]) == __ldg(&pstart[w.pc + 1]))
+        {
+            store_miss(p, pw.ray[w.slot]);
+            status = kSlotFree;
+        }
+        else
+            status = kSlotTest;
+    }
+    pw.n[0][w.slot] = w.n0; pw.n[1][w.slot] = w.n1; pw.n[2][w.slot] = w.n2;
+    pw.pc[w.slot] = w.pc;
+    pw.meta[w.slot] = (w.meta & ~kMetaStepsMask) | w.steps;
+    pw.status[w.slot] = status;
 }
 
 template <bool RCP_GUARD>
@@ -80,8 +151,8 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_pool_kernel(const __gr
 
     const uint32_t lane = threadIdx.x & 31u;
     PoolWarp& pw = pools[threadIdx.x >> 5];
-    pw.status[lane] = kSlotFree;
-    pw.status[lane + 32u] = kSlotFree;
+    for (uint32_t j = 0; j < kOwn; j++)
+        pw.status[lane + 32u * j] = kSlotFree;
     __syncwarp();
 
     PackedUnits pku;
@@ -103,17 +174,26 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_pool_kernel(const __gr
 
     for (;;)
     {
-        const uint32_t st0 = pw.status[lane], st1 = pw.status[lane + 32u];
-        const unsigned w0 = __ballot_sync(kFull, st0 == kSlotWalk), w1 = __ballot_sync(kFull, st1 == kSlotWalk);
-        const unsigned t0 = __ballot_sync(kFull, st0 == kSlotTest), t1 = __ballot_sync(kFull, st1 == kSlotTest);
-        const uint32_t n_walk = __popc(w0) + __popc(w1), n_test = __popc(t0) + __popc(t1);
+        unsigned walkers[kOwn], testers[kOwn], vacant[kOwn];
+        uint32_t n_walk = 0, n_test = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < kOwn; j++)
+        {
+            const uint32_t st = pw.status[lane + 32u * j];
+            walkers[j] = __ballot_sync(kFull, st == kSlotWalk);
+            testers[j] = __ballot_sync(kFull, st == kSlotTest);
+            vacant[j] = ~(walkers[j] | testers[j]);
+            n_walk += __popc(walkers[j]);
+            n_test += __popc(testers[j]);
+        }
         const uint32_t n_free = (uint32_t) kPoolSlots - n_walk - n_test;
-        // what 32 lanes can do together: a full round of tests, else a full round of walks, else take in new rays,
-        // else (the pool is draining, or split three ways) whichever kind there is more of
+        // What the lanes can do together: a full round of tests; else take in 32 new rays; else walk -- by then more
+        // than 32 rays stand in empty space, enough for two per lane (one's look-up is in flight while the other
+        // steps); else (the pool is draining) whichever kind there is more of
         enum { kRefill, kWalk, kTest } action;
         if (n_test >= 32u) action = kTest;
-        else if (n_walk >= 32u) action = kWalk;
         else if (more && n_free >= 32u) action = kRefill;
+        else if (n_walk >= 32u) action = kWalk;
         else if (n_walk + n_test == 0u) break;
         else action = n_test >= n_walk ? kTest : kWalk;
 
@@ -179,7 +259,7 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_pool_kernel(const __gr
             if (valid && !active)
                 store_miss(p, k); // the ray misses the grid's box (grid.cpp:182-184)
             // the i-th ray of this round takes the i-th free slot
-            pick_slots(pw, lane, st0 == kSlotFree, st1 == kSlotFree, ~(w0 | t0), ~(w1 | t1));
+            pick_slots(pw, lane, vacant);
             const unsigned need = __ballot_sync(kFull, active);
             if (active)
             {
@@ -196,68 +276,37 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_pool_kernel(const __gr
         }
         else if (action == kWalk)
         {
-            pick_slots(pw, lane, st0 == kSlotWalk, st1 == kSlotWalk, w0, w1);
-            if (lane < min(n_walk, 32u))
+            // Phase A of K1 on the distance map (warp_trace.cuh): v = distance of the cell the ray stands on -> the
+            // next v - 1 steps need no look-up; every step still does its own next_t += delta.  One step per ray and
+            // iteration, so that no lane waits for another one's run of blind steps; TWO rays per lane where the
+            // pool has them, so that one ray's look-up is in flight while the other one steps.  A ray that has
+            // arrived idles until the round's budget is used up or every ray has arrived
+            pick_slots(pw, lane, walkers);
+            const uint32_t n_round = min(n_walk, p.pool_dual ? 64u : 32u);
+            Walker wa, wb;
+            walker_load(pw, pw.list[lane < n_round ? lane : 0u], lane < n_round, lane, stride_y, stride_z, dist, wa);
+            walker_load(pw, pw.list[lane + 32u < n_round ? lane + 32u : 0u], lane + 32u < n_round, lane, stride_y, stride_z, dist, wb);
+#pragma unroll 1
+            for (uint32_t it = 0; it < p.pool_walk_steps; it++)
             {
-                const uint32_t slot_id = pw.list[lane];
-                float n0 = pw.n[0][slot_id], n1 = pw.n[1][slot_id], n2 = pw.n[2][slot_id];
-                const float dl0 = pw.dl[0][slot_id], dl1 = pw.dl[1][slot_id], dl2 = pw.dl[2][slot_id];
-                int pc = pw.pc[slot_id];
-                const uint32_t meta = pw.meta[slot_id];
-                const int c0 = (meta & kMetaNegX) ? -1 : 1;
-                const int c1 = (meta & kMetaNegY) ? -stride_y : stride_y;
-                const int c2 = (meta & kMetaNegZ) ? -stride_z : stride_z;
-                // phase A of K1 on the distance map (warp_trace.cuh): v = distance of the cell the ray stands on ->
-                // the next v - 1 steps need no look-up; every step still does its own next_t += delta
-                uint32_t steps = meta & kMetaStepsMask, looks = 0;
-                bool stop = false;
-                if (steps == 0)
-                {
-                    steps = __ldg(&dist[pc]);
-                    stop = steps == 0;
-                }
-                while (!stop)
-                {
-                    for (; steps > 1; steps--)
-                        dda_step(n0, n1, n2, dl0, dl1, dl2, pc, c0, c1, c2);
-                    dda_step(n0, n1, n2, dl0, dl1, dl2, pc, c0, c1, c2);
-                    steps = __ldg(&dist[pc]);
-                    stop = steps == 0;
-                    if (++looks >= kWalkLookups)
-                        break;
-                }
-                uint32_t status = kSlotWalk;
-                if (stop)
-                {
-                    // an occupied cell, or the padding: the ray has left the grid (grid.cpp:275-276)
-                    const uint32_t beg = __ldg(&pstart[pc]), len = __ldg(&pstart[pc + 1]) - beg;
-                    if (len == 0)
-                    {
-                        store_miss(p, pw.ray[slot_id]);
-                        status = kSlotFree;
-                    }
-                    else
-                    {
-                        pw.beg[slot_id] = beg;
-                        pw.len[slot_id] = len;
-                        status = kSlotTest;
-                    }
-                }
-                pw.n[0][slot_id] = n0; pw.n[1][slot_id] = n1; pw.n[2][slot_id] = n2;
-                pw.pc[slot_id] = pc;
-                pw.meta[slot_id] = (meta & ~kMetaStepsMask) | steps;
-                pw.status[slot_id] = status;
+                if (!__any_sync(kFull, (wa.steps | wb.steps) != 0))
+                    break;
+                walker_step(wa, dist);
+                walker_step(wb, dist);
             }
+            walker_store(p, pw, pstart, wa);
+            walker_store(p, pw, pstart, wb);
             __syncwarp();
         }
         else
         {
-            pick_slots(pw, lane, st0 == kSlotTest, st1 == kSlotTest, t0, t1);
+            pick_slots(pw, lane, testers);
             const bool mine = lane < min(n_test, 32u);
             const uint32_t slot_id = pw.list[mine ? lane : 0u];
             const float3 d = make_float3(pw.d[0][slot_id], pw.d[1][slot_id], pw.d[2][slot_id]);
             const float n0 = pw.n[0][slot_id], n1 = pw.n[1][slot_id], n2 = pw.n[2][slot_id];
-            const uint32_t beg = mine ? pw.beg[slot_id] : 0u, len = mine ? pw.len[slot_id] : 0u;
+            const int pc = pw.pc[slot_id];
+            const uint32_t beg = mine ? __ldg(&pstart[pc]) : 0u, len = mine ? __ldg(&pstart[pc + 1]) - beg : 0u;
             const uint32_t max_len = __reduce_max_sync(kFull, len);
             // next_crossing_t[step_axis] (grid.cpp:236-239,260) -- the step axis rule of dda_step
             const bool a2 = (n2 <= n0) && (n2 <= n1);

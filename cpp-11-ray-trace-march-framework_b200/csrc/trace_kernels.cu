@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kTraceMaxThreads) trace_tiles_kernel(const __g
     }
 }
 
-template <int VARIANT>
+template <int VARIANT, bool MAILBOX>
 __global__ void __launch_bounds__(128) intersect_rays_kernel(const __grid_constant__ RayBatchParams p)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(128) intersect_rays_kernel(const __grid_consta
     Hit hit;
     hit.t = hit.u = hit.v = 0.0f;
     hit.tri = 0xFFFFFFFFu;
-    const bool is_hit = grid_intersect<VARIANT, false>(p.grid, o, d, hit, nullptr);
+    const bool is_hit = grid_intersect<VARIANT, false, MAILBOX>(p.grid, o, d, hit, nullptr, p.mailbox_stats);
     p.tri[i] = is_hit ? hit.tri : 0xFFFFFFFFu;
     p.t[i] = is_hit ? hit.t : 0.0f;
     p.u[i] = is_hit ? hit.u : 0.0f;
@@ -590,15 +590,19 @@ int trace_tiles_max_blocks_per_sm(uint32_t variant, bool keep_hits, bool count, 
     RTM_DISPATCH(occupancy_one, occ_mode, threads, smem_bytes);
 }
 
-void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, cudaStream_t stream)
+void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, bool mailbox, cudaStream_t stream)
 {
     const uint32_t blocks = (p.n + 127) / 128;
     if (blocks == 0)
         return;
-    if (variant)
-        intersect_rays_kernel<1><<<blocks, 128, 0, stream>>>(p);
+    if (variant && mailbox)
+        intersect_rays_kernel<1, true><<<blocks, 128, 0, stream>>>(p);
+    else if (variant)
+        intersect_rays_kernel<1, false><<<blocks, 128, 0, stream>>>(p);
+    else if (mailbox)
+        intersect_rays_kernel<0, true><<<blocks, 128, 0, stream>>>(p);
     else
-        intersect_rays_kernel<0><<<blocks, 128, 0, stream>>>(p);
+        intersect_rays_kernel<0, false><<<blocks, 128, 0, stream>>>(p);
 }
 
 void launch_brute_force(const float *vtx, const uint32_t *tri, uint32_t num_tri, const RayBatchParams& p, cudaStream_t stream)

@@ -38,6 +38,11 @@ constexpr int kTraceMaxThreads = 1024; // launch bound (caps the kernel at 64 re
 //      grids of configs C2-C4): the test is a single LDS.U8 without shift / mask arithmetic
 //   3  distance map in global memory, read through L1   (grids too large for 1 / 2): one byte per cell holding the
 //      city-block distance to the nearest occupied cell -- a ray steps that many cells between look-ups
+// (The distance map staged in shared memory, one byte per cell on the LDS.U8 of mode 2, was measured on the res-64
+// grids: 17.2 against 10.4 ms on killeroo 4K/16 -- lanes wait for each other's runs of blind steps.  Not kept.)
+// (The DDA step on packed fp32 -- (next crossing, partial cell index as an exact float) pairs advanced by one
+// predicated FADD2 per axis instead of FADD + IADD, 7 instead of 10 instructions on paper -- was written for mode 2:
+// ptxas 12.9 does not predicate FADD2, it computes all three sums and selects, 19 instructions per step.  Not kept.)
 enum { kOccGlobalBits = 0, kOccSmemBits = 1, kOccSmemBytes = 2, kOccGlobalDist = 3 };
 
 // Kernel-side intersection variants: 0 / 1 are the ABI's (Moeller-Trumbore, plane + barycentric); 2 is
@@ -49,8 +54,8 @@ enum { kVariantMT = 0, kVariantBary = 1, kVariantMTRel = 2, kVariantMTAlt = 3, k
 
 // K7 trace_pool (pool_trace.cu): rays per warp pool, bytes of one warp's pool in shared memory, and the word of the
 // strip-counter line its scheduler counts in (word 0 is K1's, which runs behind it on the same stream)
-constexpr int kPoolSlots = 64;
-constexpr int kPoolWarpBytes = (9 + 6) * kPoolSlots * 4 + 32 * 4;
+constexpr int kPoolSlots = 96;
+constexpr int kPoolWarpBytes = (9 + 4) * kPoolSlots * 4 + 64 * 4;
 constexpr int kPoolCounterWord = 16;
 
 struct TraceParams
@@ -90,6 +95,8 @@ struct TraceParams
     uint32_t band_rows;                // rows per band
     uint32_t band_flush_units;         // a warp publishes its finished pieces once it holds this many
     uint32_t band_scope_sys;           // 1: counters / pixels may live on another GPU (system-scope release), 0: local
+    uint32_t pool_walk_steps;          // K7: DDA steps per ray in one walk round
+    uint32_t pool_dual;                // K7: walk rounds take two rays per lane when the pool has them
     uint32_t *hit_tri;                 // optional per-sample records (KEEP_HITS)
     float *hit_t, *hit_u, *hit_v;
     Counters *counters;                // optional (COUNT)
@@ -105,6 +112,7 @@ struct RayBatchParams
     const float *origins, *dirs;
     uint32_t *tri;
     float *t, *u, *v;
+    unsigned long long *mailbox_stats; // mailbox mode: [0] tests asked for, [1] answered from the mailbox (or null)
 };
 
 void launch_trace_tiles(const TraceParams& p, uint32_t variant, bool keep_hits, bool count, int grid_blocks,
@@ -116,7 +124,7 @@ size_t trace_tiles_smem_bytes(uint32_t spp, uint32_t occ_smem_words);
 // (all four required); follow it with launch_trace_tiles(variant = kVariantFromHits) on the same stream
 void launch_trace_pool(const TraceParams& p, int grid_blocks, int threads, cudaStream_t stream);
 size_t trace_pool_smem_bytes(uint32_t spp, int threads);
-void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, cudaStream_t stream);
+void launch_intersect_rays(const RayBatchParams& p, uint32_t variant, bool mailbox, cudaStream_t stream);
 void launch_sample_table(float2 *smp, uint32_t spp, cudaStream_t stream);
 void launch_ray_march(const float *vtx, const uint32_t *tri, uint32_t num_tri, uint32_t n, const float *origins,
                       const float *dirs, uint32_t *hit, float *t, cudaStream_t stream);

@@ -144,7 +144,7 @@ CONFIGS = {
     "C2": ("killeroo", 1920, 1080, 4, 64),
     "C3": ("torusknot", 1920, 1080, 16, 64),
     "C4": ("room", 3840, 2160, 16, 64),
-    "C5": ("tiger_soup", 3840, 2160, 16, 512),
+    "C5": ("tiger_soup", 3840, 2160, 16, 768),  # optimum of the density sweep (profiles/r02_c5_grid_density_sweep.txt)
     "killeroo4k": ("killeroo", 3840, 2160, 16, 64),
 }
 

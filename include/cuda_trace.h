@@ -40,6 +40,10 @@ typedef enum cuda_trace_status
 /* Ray/triangle test (reference triangle.h) */
 #define CUDA_TRACE_VARIANT_MT   0u /* IntersectRayTri, non-culling branch (triangle.h:15-107): the live one */
 #define CUDA_TRACE_VARIANT_BARY 1u /* IntersectRayTriBarycentric (triangle.h:210-226)                      */
+/* cuda_trace_intersect_rays only, OR-ed onto the variant: "mailboxing", the reference author's TODO at grid.cpp:172 --
+ * a ray remembers the outcome of its last 4 ray/triangle tests by triangle index and reuses it when the triangle
+ * turns up again in a later cell.  Same results bit for bit (the acceptance window is still evaluated per cell). */
+#define CUDA_TRACE_VARIANT_MAILBOX 0x100u
 
 #define CUDA_TRACE_FLAG_GAMMA     1u /* renderer.cpp:125-131 (#define GAMMA_CORRECTION); on in the reference */
 #define CUDA_TRACE_FLAG_KEEP_HITS 2u /* also record per-sample tri_idx,t,u,v (cuda_trace_download_hits)      */
@@ -127,9 +131,11 @@ int cuda_trace_upload_scene(cuda_trace_ctx *ctx, const float *vertices, uint32_t
                             const uint32_t *triangles, uint32_t num_triangles, uint32_t grid_res);
 
 /* Grid density heuristic for cuda_trace_upload_scene (the reference hard-codes 64 cells on the longest
- * axis, scene.cpp:7): about three cells per triangle, res = cbrt(3 T) clamped to [16, 640].  The
- * density sweep on the 50 M-triangle soup (profiles/r01_c5_grid_density_sweep.txt) has its optimum
- * at 512-640 where this gives 532; results stay bit-exact for ANY resolution (same algorithm). */
+ * axis, scene.cpp:7): about three cells per triangle, res = cbrt(3 T), while the grid's occupancy map fits in
+ * shared memory (res <= 108); about nine, res = cbrt(9 T) <= 896, for the larger grids, which the pooled-ray
+ * traversal walks through a distance map.  The density sweep on the 50 M-triangle soup
+ * (profiles/r02_c5_grid_density_sweep.txt) has its optimum at 768, which is what this gives; results stay
+ * bit-exact for ANY resolution (same algorithm). */
 uint32_t cuda_trace_suggest_grid_res(uint32_t num_triangles);
 
 /* Same, but with a grid supplied by the caller instead of built on the device (parity harness:
@@ -195,6 +201,10 @@ int cuda_trace_download_hits(cuda_trace_ctx *ctx, uint32_t *tri_idx, float *t, f
  * are n x 3 floats.  tri_idx = CUDA_TRACE_MISS on a miss. */
 int cuda_trace_intersect_rays(cuda_trace_ctx *ctx, uint32_t n, const float *origins, const float *dirs,
                               uint32_t variant, uint32_t *tri_idx, float *t, float *u, float *v);
+
+/* After a CUDA_TRACE_VARIANT_MAILBOX call: ray/triangle tests the walk asked for, and how many of them the
+ * mailbox answered */
+int cuda_trace_mailbox_stats(cuda_trace_ctx *ctx, uint64_t *tests, uint64_t *reused);
 
 /* Renderer::IntersectBruteForce (renderer.cpp:157-197): the same ray/triangle test against EVERY triangle,
  * no grid -- the reference author's own cross-check of Grid::Intersect, kept as an on-device self-check.

@@ -175,6 +175,33 @@ def test_arbitrary_rays(cuda_trace, port, scene_data):
         assert (tri != 0xFFFFFFFF).sum() > 1000
 
 
+@pytest.mark.parametrize("name,res", [("killeroo", 64), ("room", 64), ("torusknot", 64), ("tiger_soup_small", 48)])
+def test_mailboxing_mode(cuda_trace, port, scene_data, name, res):
+    """Mailboxing -- the reference author's TODO at grid.cpp:172 -- as an optional mode of the ray-batch entry point:
+    a ray reuses the outcome of a triangle it has already tested in an earlier cell.  Results must be bit-identical
+    to the plain walk and to the oracle; the statistics say how many tests the mailbox answered."""
+    sd = scene_data(name)
+    cuda_trace.upload_scene(sd.vtx, sd.tri, res)
+    ps = port.scene(sd.vtx, sd.tri, res, tight_ranges=True)
+    rs = np.random.RandomState(11)
+    n = 30000
+    g = ps.grid()
+    lo, hi = np.asarray(g["aabb_min"], np.float32), np.asarray(g["aabb_max"], np.float32)
+    o = (rs.uniform(-1.0, 1.0, (n, 3)) * 2.0 * (hi - lo) + (lo + hi) / 2).astype(np.float32)  # mostly outside the box
+    target = rs.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = target - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    for variant in (0, 1):
+        plain = cuda_trace.intersect_rays(o, d, variant)
+        boxed = cuda_trace.intersect_rays(o, d, variant, mailbox=True)
+        want = ps.intersect_rays(o, d, variant)
+        for a, b, c in zip(plain, boxed, want):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(b.view(np.uint32), c.view(np.uint32))
+        tests, reused = cuda_trace.mailbox_stats()
+        assert tests > 0 and 0 < reused < tests
+        print("%s variant %d: mailbox answered %.1f %% of %d tests" % (name, variant, 100.0 * reused / tests, tests))
+
+
 def cityblock_distance_map(occ):
     """Exact city-block distance transform of a boolean volume (distance 0 where set), clamped to 255: the
     separable two-sweep form per axis in numpy -- the checker of the device's distance map."""
