@@ -395,8 +395,9 @@ def roofline_of(name, counters, pixels, sec, world, local_rank):
     The scenes of C1-C4 / killeroo4k are L2-resident (a few MB of DRAM traffic per launch): those kernels are bound
     by instruction issue / the FP32 pipe, so the fraction is algorithmic flops against the FP32 ceiling WITHOUT FMA
     (the kernels round like the reference's FMA-free build) measured on this box in this run.  The 50 M-triangle
-    soup streams its records from HBM: there the bound is HBM and `achieved` is the MEASURED DRAM traffic of a launch
-    (ncu, profiles/dram_traffic.json) over the kernel time."""
+    soup does not fit in L2: there `achieved` is the MEASURED DRAM traffic of a launch (ncu, profiles/dram_traffic.json) over
+    the kernel time against the measured HBM bandwidth -- 3 % of it: the frame's working set is L2-sized and the kernel is
+    latency / issue bound, which `limiter` says next to the number."""
     capi = pkg("capi")
     R, Cc, T, Hh, P = counters["rays"], counters["cells"], counters["tri_tests"], counters["hits"], pixels
     alg_bytes = 8 * Cc + 40 * T + 48 * Hh + 4 * P
@@ -417,7 +418,10 @@ def roofline_of(name, counters, pixels, sec, world, local_rank):
             "frac": alg_flops / sec / 1e12 / (fp32_meas * world), "peak_kind": fp32_kind, "peak_nominal": fp32_nominal * world,
             "algorithmic_flops_per_launch": alg_flops}
     if name == "C5" and hbm is not None:
-        r = dict(hbm, bound="hbm", traffic=traffic, fp32_nonfma=fp32)
+        r = dict(hbm, bound="hbm", traffic=traffic, fp32_nonfma=fp32,
+                 limiter="neither ceiling: the pooled-ray kernel runs at ~72 % issue and ~70 % L1 utilisation with 40 % of the "
+                         "stall samples on long-scoreboard waits (distance look-ups, cold triangle records); "
+                         "profiles/r02_ncu_summary_C5_pool768.txt")
     else:
         r = dict(fp32, bound="fp32_nonfma", traffic=traffic, traffic_source=traffic_src, hbm=hbm)
     r["algorithmic_bytes_per_launch"] = alg_bytes

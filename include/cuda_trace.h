@@ -134,7 +134,7 @@ int cuda_trace_upload_scene(cuda_trace_ctx *ctx, const float *vertices, uint32_t
  * axis, scene.cpp:7): about three cells per triangle, res = cbrt(3 T), while the grid's occupancy map fits in
  * shared memory (res <= 108); about nine, res = cbrt(9 T) <= 896, for the larger grids, which the pooled-ray
  * traversal walks through a distance map.  The density sweep on the 50 M-triangle soup
- * (profiles/r02_c5_grid_density_sweep.txt) has its optimum at 768, which is what this gives; results stay
+ * (profiles/r02_c5_grid_density_sweep.txt) has its optimum at 768, where this gives 767; results stay
  * bit-exact for ANY resolution (same algorithm). */
 uint32_t cuda_trace_suggest_grid_res(uint32_t num_triangles);
 
