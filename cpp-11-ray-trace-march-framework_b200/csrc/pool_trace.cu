@@ -3,15 +3,17 @@
 //
 // K1 keeps a warp's 32 rays in lock step between its two phases: lanes that have reached an occupied cell wait
 // for the last walker (measured on the soup: 10.9 of 32 lanes walking, 18 of 32 threads per instruction overall).
-// Here a warp owns a POOL of 96 rays in shared memory and picks, round by round, 32 rays that all need the same
-// kind of work -- the active lanes are compacted by ballot / population count across the divergent DDA walks:
+// Here a warp owns a POOL of 96 rays in shared memory and picks, round by round, rays that all need the same kind of
+// work -- the active lanes are compacted by ballot / population count across the divergent DDA walks:
 //
-//   refill  32 new rays (the next round of the warp's current strip): ray generation, grid entry, DDA set-up
-//   walk    32 rays standing in empty space step through the distance map (warp_trace.cuh, kOccGlobalDist), one cell
-//           per lane and iteration, until they reach an occupied cell (-> test), leave the grid (-> miss) or the
-//           round's step budget is used up
 //   test    32 rays standing on occupied cells test their cells' pair records (test_pair_list of K1, unchanged)
 //           -> hit, or back to walking
+//   refill  32 new rays (the next round of the warp's current strip): ray generation, grid entry, DDA set-up
+//   walk    up to 64 rays standing in empty space, two per lane, step through the distance map (warp_trace.cuh,
+//           kOccGlobalDist), one cell per ray and iteration, until they reach an occupied cell (-> test), leave the
+//           grid (-> miss) or the round's step budget is used up
+// in this order of preference: by the time a warp walks it holds more than 32 walkers, so most lanes carry two and one
+// ray's look-up is in flight while the other one steps.
 //
 // Per-ray arithmetic is exactly K1's (same functions / the same included set-up), so every ray visits the same
 // cells and tests the same triangles in the same order: results are bit-identical.  Finished rays leave only their
