@@ -282,7 +282,12 @@ class GpuWorkload:
         self.signals_on = False
 
     def close(self):
-        self.ct.close()
+        # rank 0's framebuffer is mapped by the other ranks (CUDA IPC): they unmap it before rank 0 frees it
+        if self.rank != 0:
+            self.ct.close()
+        self.group.barrier()
+        if self.rank == 0:
+            self.ct.close()
         if self.pinned is not None:
             self.pinned.close()
 
