@@ -4,6 +4,10 @@
  * (rto_ray_tri, rto_ray_aabb, ... from oracle/librt_oracle.so) and adds:
  *
  *   rts_ray_walk_profile   the triangle-list length of every cell a ray visits, in order (tools/warp_walk_model.py)
+ *   rts_mailbox_walk       the walk WITH the mailbox of the product's optional mode (CUDA_TRACE_VARIANT_MAILBOX,
+ *                          csrc/rt_device.cuh): 4 entries, round-robin over the tests actually computed -- returns the
+ *                          hit and counts tests asked for / answered from the mailbox (tests/test_mailbox_model_cpu.py
+ *                          checks that results equal the plain walk and that the counts equal what the GPU reported)
  *   rts_study_ray          mailbox study  -- how often a ray re-tests a triangle it has tested within its last
  *                                            2 / 8 / 64 tests (the author's "mailboxing" TODO, grid.cpp:172)
  *                          pre-test study -- a conservative sphere reject in front of Moeller-Trumbore: the ray
@@ -147,4 +151,90 @@ int rts_study_ray(const rto_scene *sc, const float *origin, const float *dir, rt
 {
     uint32_t n = 0;
     return walk(sc, origin, dir, NULL, 0, &n, cnt);
+}
+
+/* The product's mailbox mode restated on the CPU: same walk, same 4-entry round-robin mailbox keyed by triangle index,
+ * outcome (hit, t, u, v) reused when the triangle turns up again; the acceptance window is evaluated per cell. */
+int rts_mailbox_walk(const rto_scene *sc, const float *origin, const float *dir, int variant, float *t, float *u, float *v,
+                     uint32_t *tri_idx, uint64_t *asked, uint64_t *reused)
+{
+    const rto_grid *g = &sc->grid;
+    float enter_t, leave_t, gi[3];
+    if (rto_point_in_aabb(origin, g->aabb_min, g->aabb_max))
+    {
+        enter_t = 0.0f;
+        gi[0] = origin[0]; gi[1] = origin[1]; gi[2] = origin[2];
+    }
+    else if (rto_ray_aabb(origin, dir, g->aabb_min, g->aabb_max, &enter_t, &leave_t))
+        for (int a = 0; a < 3; a++)
+            gi[a] = origin[a] + dir[a] * enter_t;
+    else
+        return 0;
+    float next_t[3], delta_t[3] = { 0.0f, 0.0f, 0.0f };
+    int step[3] = { 1, 1, 1 }, out[3], pos[3];
+    for (int a = 0; a < 3; a++)
+    {
+        out[a] = (int) g->dim[a];
+        pos[a] = to_voxel(g, gi, a);
+        if (dir[a] == 0.0f)
+            next_t[a] = FLT_MAX;
+        else if (dir[a] > 0.0f)
+        {
+            next_t[a] = enter_t + (to_pos(g, pos[a] + 1, a) - gi[a]) / dir[a];
+            delta_t[a] = g->cell_wdh / dir[a];
+        }
+        else
+        {
+            next_t[a] = enter_t + (to_pos(g, pos[a], a) - gi[a]) / dir[a];
+            delta_t[a] = -g->cell_wdh / dir[a];
+            step[a] = -1;
+            out[a] = -1;
+        }
+    }
+    uint32_t mb_id[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, mb_next = 0;
+    int mb_hit[4] = { 0, 0, 0, 0 };
+    float mb_t[4] = { 0 }, mb_u[4] = { 0 }, mb_v[4] = { 0 };
+    float best = FLT_MAX;
+    for (;;)
+    {
+        const int sa = (next_t[0] < next_t[1]) ? ((next_t[0] < next_t[2]) ? 0 : 2) : ((next_t[1] < next_t[2]) ? 1 : 2);
+        const uint64_t cell = (uint64_t) pos[0] + (uint64_t) pos[2] * g->dim[0] + (uint64_t) pos[1] * g->dim[0] * g->dim[2];
+        for (uint64_t k = g->cell_offset[cell]; k < g->cell_offset[cell + 1]; k++)
+        {
+            const uint32_t ci = g->tri_index[k];
+            float ct = 0.0f, cu = 0.0f, cv = 0.0f;
+            int hit = 0, found = 0;
+            (*asked)++;
+            for (int j = 0; j < 4; j++)
+                if (mb_id[j] == ci)
+                {
+                    found = 1;
+                    hit = mb_hit[j]; ct = mb_t[j]; cu = mb_u[j]; cv = mb_v[j];
+                }
+            if (found)
+                (*reused)++;
+            else
+            {
+                const uint32_t *tr = sc->tri + (size_t) ci * 6;
+                const float *v0 = sc->vtx + (size_t) tr[0] * 6, *v1 = sc->vtx + (size_t) tr[1] * 6, *v2 = sc->vtx + (size_t) tr[2] * 6;
+                if (variant == RTO_VARIANT_BARY)
+                    hit = rto_ray_tri_bary(origin, dir, v0, v1, v2, (const float *) (tr + 3), &ct, &cu, &cv, NULL);
+                else
+                    hit = rto_ray_tri(origin, dir, v0, v1, v2, &ct, &cu, &cv, NULL);
+                const uint32_t slot = mb_next++ % 4u;
+                mb_id[slot] = ci; mb_hit[slot] = hit; mb_t[slot] = ct; mb_u[slot] = cu; mb_v[slot] = cv;
+            }
+            if (hit && ct < best && ct < next_t[sa])
+            {
+                best = ct; *t = ct; *u = cu; *v = cv; *tri_idx = ci;
+            }
+        }
+        if (best != FLT_MAX)
+            return 1;
+        pos[sa] += step[sa];
+        if (pos[sa] == out[sa])
+            break;
+        next_t[sa] += delta_t[sa];
+    }
+    return 0;
 }
